@@ -1,0 +1,3 @@
+from .network import Unet
+
+__all__ = ["Unet"]

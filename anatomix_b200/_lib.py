@@ -1,0 +1,103 @@
+"""ctypes binding of ``include/anatomix_b200.h`` (the C ABI).
+
+Loading never compiles anything: the shared library is built in-tree by
+``anatomix_b200.build`` / ``__graft_entry__.build()``.  A missing library is a
+hard error for the engine path (there is no CPU or eager fallback behind it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libanatomix_b200.so")
+
+ANX_OK = 0
+STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "BAD_SHAPE", 3: "UNSUPPORTED", 4: "WORKSPACE",
+                5: "CUDA", 6: "NOT_READY", 7: "NO_DEVICE"}
+NORM = {"none": 0, "batch": 1, "instance": 2}
+ACT = {"none": 0, "relu": 1, "lrelu": 2}
+POOL = {"Max": 0, "Avg": 1}
+INTERP = {"nearest": 0, "trilinear": 1}
+FLAG_FORCE_SIMT = 1
+
+# every symbol include/anatomix_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "anx_engine_create", "anx_engine_destroy", "anx_engine_num_convs", "anx_engine_conv_info",
+    "anx_engine_set_conv", "anx_engine_workspace_bytes", "anx_engine_forward",
+    "anx_engine_forward_host", "anx_engine_launches_per_forward", "anx_engine_profile",
+    "anx_engine_num_buffers", "anx_engine_buffer_info", "anx_status_string",
+    "anx_engine_last_error", "anx_version", "anx_selftest",
+]
+
+
+class UnetDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("input_nc", C.c_int32), ("output_nc", C.c_int32),
+                ("num_downs", C.c_int32), ("ngf", C.c_int32), ("norm_kind", C.c_int32),
+                ("norm_eps", C.c_float), ("act_kind", C.c_int32), ("act_slope", C.c_float),
+                ("pool_kind", C.c_int32), ("interp_kind", C.c_int32), ("device", C.c_int32),
+                ("flags", C.c_uint32)]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        super().__init__(f"anatomix_b200 engine: {STATUS_NAMES.get(status, status)}"
+                         + (f": {detail}" if detail else ""))
+
+
+_lib = None
+
+
+def load():
+    """The loaded library (cached).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m anatomix_b200.build` "
+            "(the engine has no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, fp, i32, sz = C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_size_t
+    lib.anx_engine_create.argtypes = [C.POINTER(UnetDesc), C.POINTER(vp)]
+    lib.anx_engine_create.restype = i32
+    lib.anx_engine_destroy.argtypes = [vp]
+    lib.anx_engine_destroy.restype = None
+    lib.anx_engine_num_convs.argtypes = [vp]
+    lib.anx_engine_num_convs.restype = i32
+    lib.anx_engine_conv_info.argtypes = [vp, i32] + [C.POINTER(i32)] * 4
+    lib.anx_engine_conv_info.restype = i32
+    lib.anx_engine_set_conv.argtypes = [vp, i32] + [vp] * 6 + [i32]
+    lib.anx_engine_set_conv.restype = i32
+    lib.anx_engine_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+    lib.anx_engine_workspace_bytes.restype = sz
+    lib.anx_engine_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]
+    lib.anx_engine_forward.restype = i32
+    lib.anx_engine_forward_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.anx_engine_forward_host.restype = i32
+    lib.anx_engine_launches_per_forward.argtypes = [vp, i32, i32, i32, i32]
+    lib.anx_engine_launches_per_forward.restype = i32
+    lib.anx_engine_profile.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, sz, vp, fp, vp, i32,
+                                       C.POINTER(i32)]
+    lib.anx_engine_profile.restype = i32
+    lib.anx_engine_num_buffers.argtypes = [vp]
+    lib.anx_engine_num_buffers.restype = i32
+    lib.anx_engine_buffer_info.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(sz), C.POINTER(sz),
+                                           C.POINTER(i32), C.POINTER(i32)]
+    lib.anx_engine_buffer_info.restype = i32
+    lib.anx_status_string.argtypes = [i32]
+    lib.anx_status_string.restype = C.c_char_p
+    lib.anx_engine_last_error.argtypes = [vp]
+    lib.anx_engine_last_error.restype = C.c_char_p
+    lib.anx_version.restype = i32
+    lib.anx_selftest.argtypes = [i32, C.c_char_p, sz]
+    lib.anx_selftest.restype = i32
+    _lib = lib
+    return lib
+
+
+def selftest(device=0):
+    """(ok, report) of the tcgen05/TMA primitive probes."""
+    buf = C.create_string_buffer(16384)
+    st = load().anx_selftest(device, buf, len(buf))
+    return st == ANX_OK, buf.value.decode()

@@ -1,0 +1,669 @@
+// Engine behind the C ABI in include/anatomix_b200.h: layer program of the
+// anatomix U-Net (reference network.py:309-465), weight folding / packing,
+// workspace planning, TMA descriptors and the launch sequence of one forward
+// (reference network.py:530-548).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/anatomix_b200.h"
+#include "conv_umma.cuh"
+#include "simt_kernels.cuh"
+
+using namespace anx;
+
+namespace {
+
+// ------------------------------------------------------------------ utilities
+inline uint16_t f32_to_bf16_rne(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn load_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// ---------------------------------------------------------------- layer program
+enum StepKind { STEP_STEM, STEP_CONV, STEP_POOL, STEP_UP };
+
+struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
+    int module_index;         // position in the flat Sequential (state-dict key)
+    int cin, cout, ncols;     // ncols = cout rounded up to 16
+    int level;                // resolution level
+    bool has_norm, has_act, is_stem, is_final;
+    int src_buf, dst_buf, dst_group_offset;   // buffer ids (-1: network input / output)
+    // device parameters
+    bool ready = false;
+    int fold = 0, groups = 3;
+    void *d_wpack = nullptr;  // bf16 slabs (tensor-core convs) or fp32 [cin][27][cout] (stem)
+    float *d_bias = nullptr;  // [ncols]
+    size_t wpack_bytes = 0;
+};
+
+struct Buffer {               // padded planar activation buffer
+    int level, groups;
+};
+
+struct Step {
+    StepKind kind;
+    int conv = -1;                    // STEP_STEM / STEP_CONV
+    int src_buf = -1, dst_buf = -1;   // STEP_POOL / STEP_UP
+    int groups = 0, dst_group_offset = 0;
+    char name[32];
+};
+
+struct ShapePlan {            // everything that depends on (N, D, H, W, workspace)
+    int N = 0, D = 0, H = 0, W = 0;
+    void *workspace = nullptr;
+    std::vector<size_t> buf_offset;
+    std::vector<CUtensorMap> tmaps;   // per conv (unused for the stem)
+    std::vector<ConvGeom> geoms;      // per conv
+};
+
+}   // namespace
+
+struct anx_engine {
+    anx_unet_desc desc;
+    int num_sms = 148;
+    int max_smem = 0;
+    std::vector<ConvLayer> convs;
+    std::vector<Buffer> bufs;
+    std::vector<Step> steps;
+    std::mutex mu;
+    std::vector<std::shared_ptr<ShapePlan>> plans;
+    mutable std::string last_error;
+
+    anx_status fail(anx_status st, const char *fmt, ...) const {
+        char tmp[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(tmp, sizeof tmp, fmt, ap);
+        va_end(ap);
+        last_error = tmp;
+        return st;
+    }
+};
+
+#define ANX_CUDA(e, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess)                                                                    \
+            return (e)->fail(ANX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                             __FILE__, __LINE__);                                                    \
+    } while (0)
+
+namespace {
+
+int add_buffer(anx_engine *e, int level, int channels) {
+    e->bufs.push_back(Buffer{level, channels / 8});
+    return (int)e->bufs.size() - 1;
+}
+
+void add_conv(anx_engine *e, int &module_index, int cin, int cout, int level, bool last, bool stem, int src, int dst,
+              int dst_goff) {
+    const anx_unet_desc &d = e->desc;
+    ConvLayer c{};
+    c.module_index = module_index;
+    c.cin = cin;
+    c.cout = cout;
+    c.ncols = (cout + 15) / 16 * 16;
+    c.level = level;
+    c.has_norm = !last && d.norm_kind != ANX_NORM_NONE;
+    c.has_act = !last && d.act_kind != ANX_ACT_NONE;
+    c.is_stem = stem;
+    c.is_final = last;
+    c.src_buf = src;
+    c.dst_buf = dst;
+    c.dst_group_offset = dst_goff;
+    module_index += 1 + (c.has_norm ? 1 : 0) + (c.has_act ? 1 : 0);
+    Step s{};
+    s.kind = stem ? STEP_STEM : STEP_CONV;
+    s.conv = (int)e->convs.size();
+    snprintf(s.name, sizeof s.name, "conv%d_%dto%d_L%d", c.module_index, cin, cout, level);
+    e->convs.push_back(c);
+    e->steps.push_back(s);
+}
+
+// Walks the constructor logic of reference network.py:309-465 and lays out the
+// buffers: every conv writes straight into the buffer its consumer reads; the
+// second conv of encoder level i writes groups [0, w_i/8) of the level's concat
+// buffer and the decoder's upsample fills the rest (zero-copy torch.cat,
+// encoder channels first, network.py:545).
+void build_program(anx_engine *e) {
+    const anx_unet_desc &d = e->desc;
+    const int nd = d.num_downs, g = d.ngf;
+    int mi = 0;
+    std::vector<int> cat(nd), width(nd + 1);
+    for (int i = 0; i <= nd; ++i) width[i] = g << i;
+    for (int i = 0; i < nd; ++i) cat[i] = add_buffer(e, i, 3 * width[i]);
+
+    int cur = add_buffer(e, 0, g);
+    add_conv(e, mi, d.input_nc, g, 0, false, true, -1, cur, 0);
+    for (int i = 0; i < nd; ++i) {
+        int t = add_buffer(e, i, width[i]);
+        add_conv(e, mi, i == 0 ? g : width[i - 1], width[i], i, false, false, cur, t, 0);
+        add_conv(e, mi, width[i], width[i], i, false, false, t, cat[i], 0);
+        int p = add_buffer(e, i + 1, width[i]);
+        Step s{};
+        s.kind = STEP_POOL;
+        s.src_buf = cat[i];
+        s.dst_buf = p;
+        s.groups = width[i] / 8;
+        snprintf(s.name, sizeof s.name, "pool%d_L%d", mi, i);
+        e->steps.push_back(s);
+        mi += 1;
+        cur = p;
+    }
+    {
+        int t = add_buffer(e, nd, width[nd]);
+        add_conv(e, mi, width[nd - 1], width[nd], nd, false, false, cur, t, 0);
+        int u = add_buffer(e, nd, width[nd]);
+        add_conv(e, mi, width[nd], width[nd], nd, false, false, t, u, 0);
+        cur = u;
+    }
+    for (int l = nd - 1; l >= 0; --l) {
+        Step s{};
+        s.kind = STEP_UP;
+        s.src_buf = cur;
+        s.dst_buf = cat[l];
+        s.groups = width[l + 1] / 8;
+        s.dst_group_offset = width[l] / 8;
+        snprintf(s.name, sizeof s.name, "up%d_L%d", mi, l);
+        e->steps.push_back(s);
+        mi += 1;
+        int v = add_buffer(e, l, width[l]);
+        add_conv(e, mi, 3 * width[l], width[l], l, false, false, cat[l], v, 0);
+        int x = add_buffer(e, l, width[l]);
+        add_conv(e, mi, width[l], width[l], l, false, false, v, x, 0);
+        cur = x;
+    }
+    add_conv(e, mi, g, d.output_nc, 0, true, false, cur, -1, 0);
+}
+
+bool shape_ok(const anx_engine *e, int n, int d, int h, int w) {
+    const int unit = 1 << e->desc.num_downs;
+    if (n < 1 || d < 2 * unit || h < 2 * unit || w < 2 * unit) return false;
+    return d % unit == 0 && h % unit == 0 && w % unit == 0;
+}
+
+size_t buffer_bytes(const anx_engine *e, const Buffer &b, int n, int d, int h, int w) {
+    const size_t dp = (d >> b.level) + 2, hp = (h >> b.level) + 2, wp = (w >> b.level) + 2;
+    return align_up((size_t)n * b.groups * dp * hp * wp * 16, 256);
+}
+
+// Tile / pipeline configuration of one tensor-core conv at one shape.
+ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H, int W, int in_groups_total) {
+    ConvGeom g{};
+    g.N = N; g.D = D; g.H = H; g.W = W;
+    g.ncols = c.ncols;
+    g.fold = c.fold;
+    g.groups = c.groups;
+    g.cin_chunks = c.cin / 16;
+    g.in_groups_total = in_groups_total;
+    g.in_group_offset = 0;
+    // output planes per tile: as many as TMEM double buffering allows, at most 8
+    int bz = std::max(1, std::min(8, 256 / c.ncols));
+    g.acc_stages = 2;
+    bz = std::min(bz, D);
+    g.bz = bz;
+    int cols = g.acc_stages * bz * c.ncols;
+    int p2 = 32;
+    while (p2 < cols) p2 *= 2;
+    g.tmem_cols = p2;
+    g.tiles_x = (W + TILE_X - 1) / TILE_X;
+    g.tiles_y = (H + TILE_Y - 1) / TILE_Y;
+    g.tiles_z = (D + bz - 1) / bz;
+    g.tiles_per_sample = g.tiles_x * g.tiles_y * g.tiles_z;
+    g.total_tiles = g.tiles_per_sample * N;
+    g.a_lbo = (uint32_t)(bz + 2) * HALO_Y * ROW_BYTES;
+    g.a_stage_bytes = 2 * g.a_lbo;
+    g.b_rows = c.fold ? 3 * c.ncols : c.ncols;
+    g.b_stage_bytes = 9 * 32 * g.b_rows;
+    const size_t budget = (size_t)e->max_smem - sizeof(UmmaBarriers) - 1024;
+    g.a_stages = 3;
+    g.b_stages = 2;
+    while (g.a_stages > 1 && (size_t)g.a_stages * g.a_stage_bytes + 2u * g.b_stage_bytes > budget) --g.a_stages;
+    size_t left = budget - (size_t)g.a_stages * g.a_stage_bytes;
+    g.b_stages = (int)std::min<size_t>(MAX_B_STAGES, left / g.b_stage_bytes);
+    g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
+    g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
+                              sizeof(UmmaBarriers));
+    return g;
+}
+
+ActView view_of(const anx_engine *e, const ShapePlan &p, int buf, int group_offset) {
+    const Buffer &b = e->bufs[buf];
+    ActView v;
+    v.base = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(p.workspace) + p.buf_offset[buf]);
+    v.groups_total = b.groups;
+    v.group_offset = group_offset;
+    v.D = p.D >> b.level;
+    v.H = p.H >> b.level;
+    v.W = p.W >> b.level;
+    return v;
+}
+
+anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, std::shared_ptr<ShapePlan> &out) {
+    std::lock_guard<std::mutex> lock(e->mu);
+    for (auto &p : e->plans)
+        if (p->N == N && p->D == D && p->H == H && p->W == W && p->workspace == workspace) {
+            out = p;
+            return ANX_OK;
+        }
+    EncodeTiledFn encode = load_encode_tiled();
+    if (!encode) return e->fail(ANX_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+    auto p = std::make_shared<ShapePlan>();
+    p->N = N; p->D = D; p->H = H; p->W = W;
+    p->workspace = workspace;
+    size_t off = 0;
+    for (auto &b : e->bufs) {
+        p->buf_offset.push_back(off);
+        off += buffer_bytes(e, b, N, D, H, W);
+    }
+    p->tmaps.resize(e->convs.size());
+    p->geoms.resize(e->convs.size());
+    for (size_t i = 0; i < e->convs.size(); ++i) {
+        const ConvLayer &c = e->convs[i];
+        if (c.is_stem) continue;
+        const Buffer &sb = e->bufs[c.src_buf];
+        const int d = D >> c.level, h = H >> c.level, w = W >> c.level;
+        p->geoms[i] = make_geom(e, c, N, d, h, w, sb.groups);
+        const ConvGeom &g = p->geoms[i];
+        if (g.smem_bytes > (uint32_t)e->max_smem || g.a_stages < 1 || g.b_stages < 1)
+            return e->fail(ANX_ERR_UNSUPPORTED, "conv %d (%d->%d) does not fit shared memory", c.module_index, c.cin,
+                           c.cout);
+        // 4-D view of the padded planar buffer: [n*groups][zp][yp][xp*8 + ch]
+        cuuint64_t dims[4] = {(cuuint64_t)(w + 2) * 8, (cuuint64_t)(h + 2), (cuuint64_t)(d + 2),
+                              (cuuint64_t)N * sb.groups};
+        cuuint64_t strides[3] = {(cuuint64_t)(w + 2) * 16, (cuuint64_t)(w + 2) * (h + 2) * 16,
+                                 (cuuint64_t)(w + 2) * (h + 2) * (d + 2) * 16};
+        cuuint32_t box[4] = {HALO_X * 8, HALO_Y, (cuuint32_t)(g.bz + 2), 2};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        void *base = static_cast<char *>(workspace) + p->buf_offset[c.src_buf];
+        CUresult r = encode(&p->tmaps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return e->fail(ANX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for conv %d", (int)r, c.module_index);
+    }
+    if (e->plans.size() >= 8) e->plans.erase(e->plans.begin());
+    e->plans.push_back(p);
+    out = p;
+    return ANX_OK;
+}
+
+Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer &c, float *out) {
+    Epilogue ep{};
+    ep.cout = c.cout;
+    ep.bias = c.d_bias;
+    ep.act = c.has_act ? e->desc.act_kind : ANX_ACT_NONE;
+    ep.slope = e->desc.act_slope;
+    ep.stats = nullptr;
+    if (c.is_final) {
+        ep.mode = OUT_NCDHW_F32;
+        ep.out_f32 = out;
+        ep.dst.base = nullptr;
+        ep.dst.groups_total = 0;
+        ep.dst.group_offset = 0;
+        ep.dst.D = p.D; ep.dst.H = p.H; ep.dst.W = p.W;
+    } else {
+        ep.mode = OUT_PADDED_BF16;
+        ep.dst = view_of(e, p, c.dst_buf, c.dst_group_offset);
+        ep.out_f32 = nullptr;
+    }
+    return ep;
+}
+
+int grid_for(size_t work_items, int threads, int num_sms, int waves) {
+    size_t blocks = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)num_sms * waves;
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const float *in, float *out,
+                       cudaStream_t st) {
+    const bool force_simt = (e->desc.flags & ANX_FLAG_FORCE_SIMT) != 0;
+    switch (s.kind) {
+    case STEP_STEM: {
+        const ConvLayer &c = e->convs[s.conv];
+        Epilogue ep = make_epilogue(e, p, c, out);
+        const size_t vox = (size_t)p.N * p.D * p.H * p.W;
+        const int grid = grid_for(vox, 256, e->num_sms, 16);
+        const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
+        if (c.ncols == 16)
+            stem_conv_kernel<16><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+        else if (c.ncols == 32)
+            stem_conv_kernel<32><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+        else if (c.ncols == 48)
+            stem_conv_kernel<48><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+        else
+            stem_conv_kernel<64><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+        break;
+    }
+    case STEP_CONV: {
+        const ConvLayer &c = e->convs[s.conv];
+        const ConvGeom &g = p.geoms[s.conv];
+        Epilogue ep = make_epilogue(e, p, c, out);
+        if (force_simt) {
+            ActView src = view_of(e, p, c.src_buf, 0);
+            const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols / 16);
+            conv3_simt_kernel<<<grid_for(items, 128, e->num_sms, 64), 128, 0, st>>>(
+                src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
+        } else {
+            const int grid = std::min(g.total_tiles, e->num_sms);
+            conv3_umma_kernel<<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
+                                                                          (const uint8_t *)c.d_wpack, ep);
+        }
+        break;
+    }
+    case STEP_POOL: {
+        ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, 0);
+        const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
+        pool2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
+                                                                           e->desc.pool_kind);
+        break;
+    }
+    case STEP_UP: {
+        ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, s.dst_group_offset);
+        const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
+        upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
+                                                                               e->desc.interp_kind);
+        break;
+    }
+    }
+    ANX_CUDA(e, cudaGetLastError());
+    return ANX_OK;
+}
+
+anx_status check_forward_args(anx_engine *e, const void *in, const void *out, int n, int d, int h, int w,
+                              void *workspace, size_t ws_bytes) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (!in || !out) return e->fail(ANX_ERR_BAD_ARG, "null input/output pointer");
+    if (!shape_ok(e, n, d, h, w))
+        return e->fail(ANX_ERR_BAD_SHAPE,
+                       "input [%d,%d,%d,%d,%d]: each of D,H,W must be a multiple of %d and >= %d", n,
+                       e->desc.input_nc, d, h, w, 1 << e->desc.num_downs, 2 << e->desc.num_downs);
+    for (auto &c : e->convs)
+        if (!c.ready) return e->fail(ANX_ERR_NOT_READY, "conv at module index %d has no parameters", c.module_index);
+    const size_t need = anx_engine_workspace_bytes(e, n, d, h, w);
+    if (!workspace || ws_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return e->fail(ANX_ERR_WORKSPACE, "workspace %p of %zu bytes; need %zu bytes, 256-byte aligned", workspace,
+                       ws_bytes, need);
+    return ANX_OK;
+}
+
+}   // namespace
+
+// ========================================================================= C ABI
+extern "C" {
+
+int32_t anx_version(void) { return 100; }
+
+const char *anx_status_string(anx_status s) {
+    switch (s) {
+    case ANX_OK: return "ok";
+    case ANX_ERR_BAD_ARG: return "bad argument";
+    case ANX_ERR_BAD_SHAPE: return "unsupported input shape";
+    case ANX_ERR_UNSUPPORTED: return "configuration not supported by the engine";
+    case ANX_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+    case ANX_ERR_CUDA: return "CUDA error";
+    case ANX_ERR_NOT_READY: return "parameters not set";
+    case ANX_ERR_NO_DEVICE: return "no usable sm_100 device";
+    }
+    return "unknown status";
+}
+
+const char *anx_engine_last_error(const anx_engine *e) { return e ? e->last_error.c_str() : "null engine"; }
+
+anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
+    if (!desc || !out || desc->struct_size != sizeof(anx_unet_desc)) return ANX_ERR_BAD_ARG;
+    *out = nullptr;
+    if (desc->input_nc < 1 || desc->output_nc < 1 || desc->output_nc > 256 || desc->num_downs < 1 ||
+        desc->num_downs > 7 || desc->ngf < 16 || desc->ngf % 16 != 0 || (desc->ngf << desc->num_downs) > 256)
+        return ANX_ERR_UNSUPPORTED;
+    if (desc->norm_kind != ANX_NORM_NONE && desc->norm_kind != ANX_NORM_BATCH_EVAL) return ANX_ERR_UNSUPPORTED;
+    if (desc->act_kind < ANX_ACT_NONE || desc->act_kind > ANX_ACT_LEAKY) return ANX_ERR_BAD_ARG;
+    if (desc->pool_kind != ANX_POOL_MAX && desc->pool_kind != ANX_POOL_AVG) return ANX_ERR_BAD_ARG;
+    if (desc->interp_kind != ANX_INTERP_NEAREST && desc->interp_kind != ANX_INTERP_TRILINEAR) return ANX_ERR_BAD_ARG;
+    if (desc->ngf > 64 || desc->input_nc > 4) return ANX_ERR_UNSUPPORTED;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || desc->device < 0 || desc->device >= ndev) return ANX_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, desc->device) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+    if (prop.major != 10) return ANX_ERR_NO_DEVICE;   // tcgen05 kernels: sm_100a only, no fallback
+    if (cudaSetDevice(desc->device) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+
+    anx_engine *e = new anx_engine();
+    e->desc = *desc;
+    e->num_sms = prop.multiProcessorCount;
+    e->max_smem = (int)prop.sharedMemPerBlockOptin;
+    build_program(e);
+    for (auto &c : e->convs) {
+        c.fold = (!c.is_stem && 3 * c.ncols <= 256) ? 1 : 0;
+        c.groups = c.fold ? 1 : 3;
+    }
+    cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(stem_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (err != cudaSuccess) {
+        delete e;
+        return ANX_ERR_CUDA;
+    }
+    *out = e;
+    return ANX_OK;
+}
+
+void anx_engine_destroy(anx_engine *e) {
+    if (!e) return;
+    for (auto &c : e->convs) {
+        if (c.d_wpack) cudaFree(c.d_wpack);
+        if (c.d_bias) cudaFree(c.d_bias);
+    }
+    delete e;
+}
+
+int32_t anx_engine_num_convs(const anx_engine *e) { return e ? (int32_t)e->convs.size() : -1; }
+
+anx_status anx_engine_conv_info(const anx_engine *e, int32_t k, int32_t *module_index, int32_t *cin, int32_t *cout,
+                                int32_t *has_norm) {
+    if (!e || k < 0 || k >= (int)e->convs.size()) return ANX_ERR_BAD_ARG;
+    const ConvLayer &c = e->convs[k];
+    if (module_index) *module_index = c.module_index;
+    if (cin) *cin = c.cin;
+    if (cout) *cout = c.cout;
+    if (has_norm) *has_norm = c.has_norm ? 1 : 0;
+    return ANX_OK;
+}
+
+anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, const float *bias,
+                               const float *bn_w, const float *bn_b, const float *bn_mean, const float *bn_var,
+                               int32_t location) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (k < 0 || k >= (int)e->convs.size() || !weight) return e->fail(ANX_ERR_BAD_ARG, "bad conv ordinal or null weight");
+    ConvLayer &c = e->convs[k];
+    const bool fold_bn = c.has_norm && e->desc.norm_kind == ANX_NORM_BATCH_EVAL;
+    if (fold_bn && (!bn_w || !bn_b || !bn_mean || !bn_var))
+        return e->fail(ANX_ERR_BAD_ARG, "conv %d is followed by BatchNorm: its four arrays are required", c.module_index);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    const size_t nw = (size_t)c.cout * c.cin * 27;
+    std::vector<float> hw(nw), hb, g1, g2, g3, g4;
+    auto fetch = [&](const float *src, std::vector<float> &dst, size_t n) -> cudaError_t {
+        dst.resize(n);
+        if (location == ANX_LOC_DEVICE) return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost);
+        std::memcpy(dst.data(), src, n * sizeof(float));
+        return cudaSuccess;
+    };
+    ANX_CUDA(e, fetch(weight, hw, nw));
+    if (bias) ANX_CUDA(e, fetch(bias, hb, c.cout));
+    std::vector<float> scale(c.cout, 1.0f), shift(c.ncols, 0.0f);
+    if (fold_bn) {
+        ANX_CUDA(e, fetch(bn_w, g1, c.cout));
+        ANX_CUDA(e, fetch(bn_b, g2, c.cout));
+        ANX_CUDA(e, fetch(bn_mean, g3, c.cout));
+        ANX_CUDA(e, fetch(bn_var, g4, c.cout));
+        // eval BatchNorm folded into the conv: y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
+        for (int o = 0; o < c.cout; ++o) {
+            scale[o] = g1[o] / std::sqrt(g4[o] + e->desc.norm_eps);
+            shift[o] = g2[o] - g3[o] * scale[o] + (bias ? hb[o] * scale[o] : 0.0f);
+        }
+    } else if (bias) {
+        for (int o = 0; o < c.cout; ++o) shift[o] = hb[o];
+    }
+
+    if (c.d_wpack) { cudaFree(c.d_wpack); c.d_wpack = nullptr; }
+    if (c.d_bias) { cudaFree(c.d_bias); c.d_bias = nullptr; }
+    c.ready = false;
+    if (c.is_stem) {
+        // fp32 [cin][27][ncols]
+        std::vector<float> pk((size_t)c.cin * 27 * c.ncols, 0.0f);
+        for (int o = 0; o < c.cout; ++o)
+            for (int i = 0; i < c.cin; ++i)
+                for (int t = 0; t < 27; ++t)
+                    pk[((size_t)i * 27 + t) * c.ncols + o] = hw[((size_t)o * c.cin + i) * 27 + t] * scale[o];
+        c.wpack_bytes = pk.size() * sizeof(float);
+        ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
+        ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
+    } else {
+        // bf16 slabs [chunk][group][tap(ky,kx)][kchunk][row][8]; folded rows = (dz=+1 | 0 | -1) x ncols
+        const int R = c.fold ? 3 * c.ncols : c.ncols;
+        const int chunks = c.cin / 16;
+        const size_t slab = (size_t)9 * 2 * R * 8;
+        std::vector<uint16_t> pk((size_t)chunks * c.groups * slab, 0);
+        for (int o = 0; o < c.cout; ++o)
+            for (int i = 0; i < c.cin; ++i) {
+                const int ch = i / 16, kc = (i % 16) / 8, el = i % 8;
+                for (int kz = 0; kz < 3; ++kz) {
+                    const int grp = c.fold ? 0 : kz;
+                    const int row = c.fold ? (2 - kz) * c.ncols + o : o;
+                    for (int t = 0; t < 9; ++t) {
+                        const float v = hw[((size_t)o * c.cin + i) * 27 + kz * 9 + t] * scale[o];
+                        pk[(size_t)(ch * c.groups + grp) * slab + ((size_t)(t * 2 + kc) * R + row) * 8 + el] =
+                            f32_to_bf16_rne(v);
+                    }
+                }
+            }
+        c.wpack_bytes = pk.size() * sizeof(uint16_t);
+        ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
+        ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
+    }
+    ANX_CUDA(e, cudaMalloc(&c.d_bias, c.ncols * sizeof(float)));
+    ANX_CUDA(e, cudaMemcpy(c.d_bias, shift.data(), c.ncols * sizeof(float), cudaMemcpyHostToDevice));
+    c.ready = true;
+    return ANX_OK;
+}
+
+size_t anx_engine_workspace_bytes(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w) {
+    if (!e || !shape_ok(e, n, d, h, w)) return 0;
+    size_t total = 0;
+    for (auto &b : e->bufs) total += buffer_bytes(e, b, n, d, h, w);
+    return total;
+}
+
+anx_status anx_engine_buffer_info(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w, int32_t index,
+                                  size_t *offset, size_t *bytes, int32_t *level, int32_t *groups) {
+    if (!e || !shape_ok(e, n, d, h, w) || index < 0 || index >= (int)e->bufs.size()) return ANX_ERR_BAD_ARG;
+    size_t off = 0;
+    for (int i = 0; i < index; ++i) off += buffer_bytes(e, e->bufs[i], n, d, h, w);
+    if (offset) *offset = off;
+    if (bytes) *bytes = buffer_bytes(e, e->bufs[index], n, d, h, w);
+    if (level) *level = e->bufs[index].level;
+    if (groups) *groups = e->bufs[index].groups;
+    return ANX_OK;
+}
+
+int32_t anx_engine_num_buffers(const anx_engine *e) { return e ? (int32_t)e->bufs.size() : -1; }
+
+int32_t anx_engine_launches_per_forward(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w) {
+    if (!e || !shape_ok(e, n, d, h, w)) return -1;
+    return (int32_t)e->steps.size();
+}
+
+anx_status anx_engine_forward(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                              void *workspace, size_t ws_bytes, void *stream) {
+    anx_status st = check_forward_args(e, in, out, n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    for (auto &s : e->steps) {
+        st = launch_step(e, *p, s, in, out, static_cast<cudaStream_t>(stream));
+        if (st != ANX_OK) return st;
+    }
+    return ANX_OK;
+}
+
+anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *out_host, int32_t n, int32_t d,
+                                   int32_t h, int32_t w, float *dev_in, float *dev_out, void *workspace,
+                                   size_t ws_bytes, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (!in_host || !out_host || !dev_in || !dev_out) return e->fail(ANX_ERR_BAD_ARG, "null buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t vox = (size_t)n * d * h * w;
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    ANX_CUDA(e, cudaMemcpyAsync(dev_in, in_host, vox * e->desc.input_nc * sizeof(float), cudaMemcpyHostToDevice, st));
+    anx_status r = anx_engine_forward(e, dev_in, dev_out, n, d, h, w, workspace, ws_bytes, stream);
+    if (r != ANX_OK) return r;
+    ANX_CUDA(e, cudaMemcpyAsync(out_host, dev_out, vox * e->desc.output_nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return ANX_OK;
+}
+
+anx_status anx_engine_profile(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                              void *workspace, size_t ws_bytes, void *stream, float *ms_out, char (*names)[32],
+                              int32_t capacity, int32_t *count) {
+    anx_status st = check_forward_args(e, in, out, n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    if (!ms_out || !names || !count) return e->fail(ANX_ERR_BAD_ARG, "null profile outputs");
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int k = (int)e->steps.size();
+    std::vector<cudaEvent_t> ev(k + 1);
+    for (auto &x : ev) ANX_CUDA(e, cudaEventCreate(&x));
+    ANX_CUDA(e, cudaEventRecord(ev[0], s));
+    for (int i = 0; i < k; ++i) {
+        st = launch_step(e, *p, e->steps[i], in, out, s);
+        if (st != ANX_OK) return st;
+        ANX_CUDA(e, cudaEventRecord(ev[i + 1], s));
+    }
+    ANX_CUDA(e, cudaStreamSynchronize(s));
+    *count = std::min(k, capacity);
+    for (int i = 0; i < *count; ++i) {
+        ANX_CUDA(e, cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+        std::memcpy(names[i], e->steps[i].name, 32);
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+    return ANX_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,83 @@
+// Activation layout in HBM and the parameter blocks shared by the kernels.
+//
+// Every intermediate activation lives in a reflect-PADDED, channel-group-planar
+// bf16 buffer:
+//
+//      [n][g][zp][yp][xp][8]      zp in [0, D+2), yp in [0, H+2), xp in [0, W+2)
+//
+// g indexes groups of 8 channels (16 bytes per voxel per group).  The one-voxel
+// shell holds the reflect padding of nn.Conv3d(padding_mode='reflect')
+// (reference network.py:310-318): shell[0] = interior[1], shell[S+1] =
+// interior[S-2], written by the PRODUCER of the tensor, so every conv is a plain
+// "valid" 3x3x3 correlation on the padded buffer.  16-byte voxels with x
+// contiguous are exactly the 8x16-byte "core matrix" rows a K-major,
+// non-swizzled tcgen05 shared-memory descriptor wants, so a TMA box copy of a
+// halo brick is directly a valid A operand for all 27 taps.
+//
+// A skip concat (network.py:545) is zero-copy: the encoder conv and the
+// upsample write disjoint group ranges [0, Cskip/8) and [Cskip/8, ...) of one
+// buffer.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace anx {
+
+struct ActView {            // one tensor inside a padded planar buffer
+    __nv_bfloat16 *base;    // start of the whole buffer
+    int groups_total;       // channel groups per sample in the buffer
+    int group_offset;       // first group of this tensor
+    int D, H, W;            // interior size
+    __host__ __device__ __forceinline__ size_t voxel_index(int n, int g, int zp, int yp, int xp) const {
+        return ((((size_t)n * groups_total + (group_offset + g)) * (D + 2) + zp) * (H + 2) + yp) * (size_t)(W + 2) + xp;
+    }
+    __host__ __device__ __forceinline__ uint4 *at(int n, int g, int zp, int yp, int xp) const {
+        return reinterpret_cast<uint4 *>(base) + voxel_index(n, g, zp, yp, xp);
+    }
+};
+
+enum OutMode : int {
+    OUT_PADDED_BF16 = 0,    // next layer's padded planar buffer (+ reflect shell)
+    OUT_NCDHW_F32 = 1       // network output, fp32 [N, C, D, H, W]
+};
+
+struct Epilogue {
+    int mode;
+    ActView dst;            // OUT_PADDED_BF16
+    float *out_f32;         // OUT_NCDHW_F32
+    int cout;               // real output channels (<= padded ncols)
+    const float *bias;      // [ncols] folded BN shift / conv bias (zeros if none)
+    int act;                // 0 none, 1 relu, 2 leaky
+    float slope;
+    float *stats;           // instance-norm partial sums [N][ncols][2] (sum, sumsq) or nullptr
+};
+
+// tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),
+// `bz` output planes per CTA tile.
+constexpr int TILE_X = 8;
+constexpr int TILE_Y = 16;
+constexpr int HALO_X = TILE_X + 2;      // 10
+constexpr int HALO_Y = TILE_Y + 2;      // 18
+constexpr int ROW_BYTES = HALO_X * 16;  // 160: one x-row of the halo brick per group
+
+struct ConvGeom {
+    int N, D, H, W;
+    int tiles_x, tiles_y, tiles_z, tiles_per_sample, total_tiles;
+    int bz;                 // output planes per tile
+    int cin_chunks;         // Cin / 16
+    int in_groups_total;    // groups per sample in the INPUT buffer (TMA dim 3 = n * this + g)
+    int in_group_offset;
+    int ncols;              // Cout rounded up to 16 (TMEM columns per output plane)
+    int fold;               // 1: one MMA covers the three dz taps (N = 3*ncols)
+    int groups;             // B stages per chunk: 1 when folded, 3 (one per dz) otherwise
+    int acc_stages;         // TMEM accumulator double buffering
+    int tmem_cols;          // power of two >= acc_stages * bz * ncols
+    int a_stages, b_stages;
+    uint32_t a_stage_bytes; // 2 * (bz+2) * HALO_Y * ROW_BYTES
+    uint32_t a_lbo;         // (bz+2) * HALO_Y * ROW_BYTES : distance between the two 8-channel planes
+    uint32_t b_stage_bytes; // 9 * 32 * R, R = rows per tap matrix
+    uint32_t b_rows;        // R = fold ? 3*ncols : ncols
+    uint32_t smem_bytes;
+};
+
+}   // namespace anx

@@ -1,0 +1,259 @@
+"""Python host side of the B200 engine: an `Engine` object over the C ABI
+(``include/anatomix_b200.h``) plus the glue that lets the `Unet` module hand
+eligible forwards to it.
+
+torch is used here only as plumbing: device memory (workspace / output
+tensors from the caching allocator), the current CUDA stream, and reading the
+module's parameters.  All arithmetic of an eligible forward happens inside
+``libanatomix_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import EngineError
+
+
+def _desc_from_cfg(cfg: dict, device_index: int, flags: int = 0) -> _lib.UnetDesc:
+    d = _lib.UnetDesc()
+    d.struct_size = C.sizeof(_lib.UnetDesc)
+    d.input_nc, d.output_nc = cfg["input_nc"], cfg["output_nc"]
+    d.num_downs, d.ngf = cfg["num_downs"], cfg.get("ngf", 24)
+    d.norm_kind = _lib.NORM[cfg.get("norm", "batch")]
+    d.norm_eps = cfg.get("norm_eps", 1e-5)
+    d.act_kind = _lib.ACT[cfg.get("activation", "relu")]
+    d.act_slope = 0.3                      # reference network.py:191
+    d.pool_kind = _lib.POOL[cfg.get("pooling", "Max")]
+    d.interp_kind = _lib.INTERP[cfg.get("interp", "nearest")]
+    d.device = device_index
+    d.flags = flags
+    return d
+
+
+class Engine:
+    """One network on one CUDA device.  ``cfg`` holds the reference constructor
+    kwargs (network.py:262-279); parameters arrive via `load_state`."""
+
+    def __init__(self, cfg: dict, device: torch.device | int | str = "cuda", flags: int = 0):
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("the engine runs on CUDA devices only")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.cfg = dict(cfg)
+        self._h = C.c_void_p()
+        desc = _desc_from_cfg(cfg, self.device.index, flags)
+        with torch.cuda.device(self.device):
+            st = self.lib.anx_engine_create(C.byref(desc), C.byref(self._h))
+        if st != _lib.ANX_OK:
+            raise EngineError(st, self.lib.anx_status_string(st).decode())
+        self.output_nc = cfg["output_nc"]
+        self.input_nc = cfg["input_nc"]
+        self._workspaces: Dict[tuple, torch.Tensor] = {}
+
+    # -- lifetime ----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.anx_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != _lib.ANX_OK:
+            raise EngineError(st, self.lib.anx_engine_last_error(self._h).decode())
+
+    # -- parameters ----------------------------------------------------------
+    def conv_table(self):
+        """[(module_index, cin, cout, has_norm)] in network order."""
+        out = []
+        for k in range(self.lib.anx_engine_num_convs(self._h)):
+            v = [C.c_int32() for _ in range(4)]
+            self._check(self.lib.anx_engine_conv_info(self._h, k, *[C.byref(x) for x in v]))
+            out.append(tuple(x.value for x in v))
+        return out
+
+    def load_state(self, state: dict):
+        """Feeds a reference-format state dict (``model.<idx>.weight`` ...)."""
+        norm = self.cfg.get("norm", "batch")
+        for k, (idx, cin, cout, has_norm) in enumerate(self.conv_table()):
+            def host(name):
+                t = torch.as_tensor(state[name]).detach().to("cpu", torch.float32).contiguous()
+                return t
+            w = host(f"model.{idx}.weight")
+            if tuple(w.shape) != (cout, cin, 3, 3, 3):
+                raise ValueError(f"model.{idx}.weight has shape {tuple(w.shape)}, expected {(cout, cin, 3, 3, 3)}")
+            keep = [w]
+            b = None
+            if f"model.{idx}.bias" in state:
+                b = host(f"model.{idx}.bias"); keep.append(b)
+            bn = [None] * 4
+            if has_norm and norm == "batch":
+                bn = [host(f"model.{idx + 1}.{n}") for n in ("weight", "bias", "running_mean", "running_var")]
+                keep += bn
+            ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+            with torch.cuda.device(self.device):
+                self._check(self.lib.anx_engine_set_conv(self._h, k, ptr(w), ptr(b), *[ptr(t) for t in bn], 0))
+
+    # -- forward ---------------------------------------------------------------
+    def workspace_bytes(self, n, d, h, w) -> int:
+        return self.lib.anx_engine_workspace_bytes(self._h, n, d, h, w)
+
+    def launches_per_forward(self, n, d, h, w) -> int:
+        return self.lib.anx_engine_launches_per_forward(self._h, n, d, h, w)
+
+    def _shape_error(self, shape):
+        unit = 1 << self.cfg["num_downs"]
+        return ValueError(
+            f"input of shape {tuple(shape)} is not usable by this U-Net: each of D, H, W must be a "
+            f"multiple of {unit} and at least {2 * unit} (the reference fails on such shapes too)")
+
+    def workspace(self, n, d, h, w) -> torch.Tensor:
+        key = (n, d, h, w)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            need = self.workspace_bytes(n, d, h, w)
+            if need == 0:
+                raise self._shape_error((n, self.input_nc, d, h, w))
+            if len(self._workspaces) >= 4:
+                self._workspaces.pop(next(iter(self._workspaces)))
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._workspaces[key] = ws
+        return ws
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 NCDHW CUDA tensor in, fp32 NCDHW CUDA tensor out, queued on the
+        current stream of the engine's device."""
+        if x.dim() != 5 or x.shape[1] != self.input_nc:
+            raise ValueError(f"expected input [N, {self.input_nc}, D, H, W], got {tuple(x.shape)}")
+        if x.device != self.device:
+            raise ValueError(f"input on {x.device}, engine on {self.device}")
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        if out is None:
+            out = torch.empty((n, self.output_nc, d, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
+                     dev_out: torch.Tensor):
+        """End-to-end call on (pinned) host buffers; see anx_engine_forward_host."""
+        n, _, d, h, w = x_host.shape
+        ws = self.workspace(n, d, h, w)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_host(
+                self._h, x_host.data_ptr(), out_host.data_ptr(), n, d, h, w, dev_in.data_ptr(),
+                dev_out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+
+    def profile(self, x: torch.Tensor):
+        """[(step name, milliseconds)] of one forward, CUDA-event timed per launch."""
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        out = torch.empty((n, self.output_nc, d, h, w), dtype=torch.float32, device=self.device)
+        cap = 256
+        ms = (C.c_float * cap)()
+        names = C.create_string_buffer(32 * cap)
+        cnt = C.c_int32()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_profile(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream,
+                ms, names, cap, C.byref(cnt)))
+        raw = names.raw
+        return [(raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), ms[i]) for i in range(cnt.value)]
+
+    def buffer_table(self, n, d, h, w):
+        """[(offset, bytes, level, groups)] of the workspace's activation buffers."""
+        out = []
+        for i in range(self.lib.anx_engine_num_buffers(self._h)):
+            off, nb, lvl, grp = C.c_size_t(), C.c_size_t(), C.c_int32(), C.c_int32()
+            self._check(self.lib.anx_engine_buffer_info(self._h, n, d, h, w, i, C.byref(off), C.byref(nb),
+                                                        C.byref(lvl), C.byref(grp)))
+            out.append((off.value, nb.value, lvl.value, grp.value))
+        return out
+
+
+# --------------------------------------------------------------------- eligibility
+def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[str]:
+    """Why a call must stay on the stock torch path, or None if the engine takes
+    it."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        return "input is not a CUDA tensor"
+    if len(layers) > 0:
+        return "feature taps requested"
+    if cfg["dimension"] != 3 or x.dim() != 5:
+        return "not a 3-D network / 5-D input"
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        return "autograd is recording"
+    if torch.is_autocast_enabled():
+        return "autocast region"
+    if cfg["pad_type"] != "reflect" or not cfg["doubleconv"] or not cfg["use_skip_connection"] \
+            or cfg["residual_connection"] or cfg["final_act"] != "none":
+        return "non-released topology flags"
+    if cfg["norm"] == "batch":
+        if module.training:
+            return "BatchNorm in train mode uses batch statistics"
+    elif cfg["norm"] != "none":
+        return f"norm {cfg['norm']!r} not on the engine yet"
+    if cfg["activation"] not in ("relu", "lrelu", "none"):
+        return "activation not supported"
+    if cfg["pooling"] not in ("Max", "Avg") or cfg["interp"] not in ("nearest", "trilinear"):
+        return "pooling / interpolation not supported"
+    if cfg["ngf"] % 16 != 0 or cfg["ngf"] > 64 or (cfg["ngf"] << cfg["num_downs"]) > 256 \
+            or cfg["input_nc"] > 4 or cfg["output_nc"] > 256:
+        return "channel widths outside the tensor-core kernel's range"
+    if x.shape[1] != cfg["input_nc"]:
+        return "channel mismatch"
+    unit = 1 << cfg["num_downs"]
+    if any(s % unit != 0 or s < 2 * unit for s in x.shape[2:]):
+        return "spatial size not a multiple of 2^num_downs (the reference fails here too)"
+    if x.dtype != torch.float32:
+        return "input is not fp32"
+    return None
+
+
+class ModuleBinding:
+    """Keeps one `Engine` per device in sync with a live ``nn.Module``: packed
+    weights are rebuilt whenever a parameter or buffer changed (``_version`` bump
+    from ``load_state_dict`` / an optimizer step, or new storage from ``.to()``)."""
+
+    def __init__(self, module: nn.Module, cfg: dict):
+        self.module = module
+        self.cfg = cfg
+        self.engines: Dict[torch.device, Engine] = {}
+        self.stamps: Dict[torch.device, tuple] = {}
+
+    def _stamp(self):
+        return tuple((t.data_ptr(), t._version) for t in
+                     list(self.module.parameters()) + list(self.module.buffers()))
+
+    def engine_for(self, device: torch.device) -> Engine:
+        eng = self.engines.get(device)
+        if eng is None:
+            eng = Engine(self.cfg, device)
+            self.engines[device] = eng
+        stamp = self._stamp()
+        if self.stamps.get(device) != stamp:
+            eng.load_state(self.module.state_dict())
+            self.stamps[device] = stamp
+        return eng
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.engine_for(x.device).forward(x)

@@ -1,0 +1,156 @@
+/* anatomix_b200 -- C ABI of the B200 (sm_100a) U-Net forward engine.
+ *
+ * Drop-in boundary for ONE hot path of neel-dey/anatomix: the standard branch of
+ * `Unet.forward` (reference anatomix/model/network.py:530-548) of the network
+ * built by `Unet.__init__` (network.py:262-465).  The reference has no FFI of its
+ * own (it is pure Python over torch.nn); the entry points below are what a
+ * binding for this path needs: describe the network the constructor would
+ * build, hand over each conv's parameters (the state-dict tensors
+ * `model.<idx>.weight/.bias` and the following norm's
+ * `weight/bias/running_mean/running_var`), then run forwards on caller-owned
+ * device (or host) buffers.  Plain C types only; no torch types, no exceptions,
+ * no allocation on the forward path, nothing aborts.
+ *
+ * Layout contract (same as the reference module):
+ *   input   fp32  NCDHW  [N, input_nc, D, H, W]   contiguous
+ *   output  fp32  NCDHW  [N, output_nc, D, H, W]  contiguous
+ *   each of D, H, W a multiple of 2^num_downs and >= 2 * 2^num_downs
+ *   (smaller / ragged shapes fail in the reference too: reflect padding of a
+ *   size-1 bottleneck, or a pool/upsample size mismatch at the skip concat).
+ */
+#ifndef ANATOMIX_B200_H
+#define ANATOMIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct anx_engine anx_engine;
+
+typedef enum anx_status {
+    ANX_OK = 0,
+    ANX_ERR_BAD_ARG = 1,       /* null pointer, bad ordinal, bad enum            */
+    ANX_ERR_BAD_SHAPE = 2,     /* N/D/H/W not usable with this network depth     */
+    ANX_ERR_UNSUPPORTED = 3,   /* configuration outside the engine's fast path   */
+    ANX_ERR_WORKSPACE = 4,     /* workspace null / too small / misaligned        */
+    ANX_ERR_CUDA = 5,          /* a CUDA call failed; see anx_engine_last_error  */
+    ANX_ERR_NOT_READY = 6,     /* forward before every conv was set              */
+    ANX_ERR_NO_DEVICE = 7      /* no sm_100 device / driver entry point missing  */
+} anx_status;
+
+enum { ANX_NORM_NONE = 0, ANX_NORM_BATCH_EVAL = 1, ANX_NORM_INSTANCE = 2 };
+enum { ANX_ACT_NONE = 0, ANX_ACT_RELU = 1, ANX_ACT_LEAKY = 2 };
+enum { ANX_POOL_MAX = 0, ANX_POOL_AVG = 1 };
+enum { ANX_INTERP_NEAREST = 0, ANX_INTERP_TRILINEAR = 1 };
+enum { ANX_LOC_HOST = 0, ANX_LOC_DEVICE = 1 };
+
+/* Mirrors the constructor arguments of reference network.py:262-279 that the
+ * engine supports (dimension=3, pad_type='reflect', doubleconv=True,
+ * use_skip_connection=True, residual_connection=False, final_act='none'). */
+typedef struct anx_unet_desc {
+    uint32_t struct_size;   /* = sizeof(anx_unet_desc), for forward compatibility   */
+    int32_t input_nc;       /* network.py:265                                       */
+    int32_t output_nc;      /* network.py:266                                       */
+    int32_t num_downs;      /* network.py:267                                       */
+    int32_t ngf;            /* network.py:268; must be a multiple of 16             */
+    int32_t norm_kind;      /* ANX_NORM_*: 'batch' in eval mode / 'instance' / none */
+    float   norm_eps;       /* network.py:278                                       */
+    int32_t act_kind;       /* ANX_ACT_*: 'relu' / 'lrelu' / 'none'                 */
+    float   act_slope;      /* 0.3 for 'lrelu' (network.py:191)                     */
+    int32_t pool_kind;      /* ANX_POOL_*    (network.py:297)                       */
+    int32_t interp_kind;    /* ANX_INTERP_*  (network.py:407)                       */
+    int32_t device;         /* CUDA device ordinal the engine lives on              */
+    uint32_t flags;         /* ANX_FLAG_* below                                     */
+} anx_unet_desc;
+
+/* debugging / measurement switches */
+#define ANX_FLAG_FORCE_SIMT 1u   /* run every conv on the CUDA-core debug kernel  */
+
+/* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
+ * device constants; no parameters yet. */
+anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out_engine);
+void anx_engine_destroy(anx_engine *engine);
+
+/* Number of convolutions in network order (20 for `anatomix`, 24 for
+ * `anatomix-dev`) and the shape of each, so a binding can check its state dict. */
+int32_t anx_engine_num_convs(const anx_engine *engine);
+anx_status anx_engine_conv_info(const anx_engine *engine, int32_t ordinal,
+                                int32_t *module_index, int32_t *cin, int32_t *cout,
+                                int32_t *has_norm);
+
+/* Replaces: load_state_dict for one conv block (load_from_hf.py:48).
+ * `weight` is `model.<idx>.weight` fp32 [cout, cin, 3, 3, 3]; `bias` is
+ * `model.<idx>.bias` or NULL (network.py:292); the four bn_* arrays are the
+ * following BatchNorm3d's weight / bias / running_mean / running_var (all NULL
+ * unless norm_kind == ANX_NORM_BATCH_EVAL and the conv has a norm).  The engine
+ * folds, rounds and repacks into its own device buffers; the caller keeps
+ * ownership of the inputs.  `location` says whether the pointers are host or
+ * device memory.  Not thread-safe against concurrent forwards. */
+anx_status anx_engine_set_conv(anx_engine *engine, int32_t ordinal,
+                               const float *weight, const float *bias,
+                               const float *bn_weight, const float *bn_bias,
+                               const float *bn_running_mean, const float *bn_running_var,
+                               int32_t location);
+
+/* Scratch the forward needs for a given input shape (activations between
+ * layers; caller-owned so torch's caching allocator can serve it).  0 on a bad
+ * shape.  Must be 256-byte aligned. */
+size_t anx_engine_workspace_bytes(const anx_engine *engine, int32_t n, int32_t d,
+                                  int32_t h, int32_t w);
+
+/* Replaces: Unet.forward standard branch (network.py:530-548) with device
+ * buffers.  Asynchronous on `stream` (a cudaStream_t); no allocation, no
+ * synchronisation.  Distinct workspaces allow concurrent calls. */
+anx_status anx_engine_forward(anx_engine *engine, const float *in_ncdhw, float *out_ncdhw,
+                              int32_t n, int32_t d, int32_t h, int32_t w,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same call for HOST buffers (pinned memory recommended): copies the input to
+ * `dev_in`, runs the forward, copies `dev_out` back, all queued on `stream`.
+ * `dev_in` / `dev_out` are caller-owned device staging buffers of the input /
+ * output size.  This is the end-to-end entry point bench.py times. */
+anx_status anx_engine_forward_host(anx_engine *engine, const float *in_host, float *out_host,
+                                   int32_t n, int32_t d, int32_t h, int32_t w,
+                                   float *dev_in, float *dev_out,
+                                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernel launches one forward of this shape issues (for bench.py's
+ * `gpu_launches`); -1 on a bad shape. */
+int32_t anx_engine_launches_per_forward(const anx_engine *engine, int32_t n, int32_t d,
+                                        int32_t h, int32_t w);
+
+/* Per-conv timing hook for profiling: runs the forward once with CUDA events
+ * around every launch and writes `count` (<= capacity) milliseconds into
+ * `ms_out` plus a short name into `names_out[i][32]`.  Synchronises. */
+anx_status anx_engine_profile(anx_engine *engine, const float *in_ncdhw, float *out_ncdhw,
+                              int32_t n, int32_t d, int32_t h, int32_t w,
+                              void *workspace, size_t workspace_bytes, void *stream,
+                              float *ms_out, char (*names_out)[32], int32_t capacity,
+                              int32_t *count);
+
+/* Introspection of the workspace layout (tests / debugging): activation buffer
+ * `index` holds `groups` 8-channel groups of a reflect-padded planar bf16 tensor
+ * [n][g][D/2^level+2][H/2^level+2][W/2^level+2][8] at `offset` in the workspace. */
+int32_t anx_engine_num_buffers(const anx_engine *engine);
+anx_status anx_engine_buffer_info(const anx_engine *engine, int32_t n, int32_t d, int32_t h,
+                                  int32_t w, int32_t index, size_t *offset, size_t *bytes,
+                                  int32_t *level, int32_t *groups);
+
+const char *anx_status_string(anx_status status);
+/* Detail of the last failure on this engine (thread-unsafe convenience). */
+const char *anx_engine_last_error(const anx_engine *engine);
+int32_t anx_version(void);
+
+/* Self-test of the tcgen05 / TMA primitives the conv kernel relies on (small
+ * GEMM through hand-built shared-memory descriptors, a TMA brick load and one
+ * conv tile against a CUDA-core reference).  Returns ANX_OK when every probe
+ * matches; writes a human-readable report (NUL-terminated) into `report`. */
+anx_status anx_selftest(int32_t device, char *report, size_t report_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANATOMIX_B200_H */

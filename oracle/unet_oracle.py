@@ -1,0 +1,211 @@
+"""CPU ORACLE (test infrastructure, never shipped, never on the product path).
+
+A functional restatement of ``anatomix.model.network.Unet.forward`` (reference
+``anatomix/model/network.py:467-548``) for 3-D inputs, written against
+``torch.nn.functional`` on the CPU.  The reference keeps no arithmetic of its own:
+every op is a ``torch.nn`` layer (torch==2.13.0 pinned in the reference's
+``requirements.txt:10``; torch 2.11.0 CPU in this image, same operator
+semantics), so the restatement calls the same ATen operators at the same call
+sites and re-derives the flat layer order from the constructor logic
+(network.py:309-465) independently of the product's `anatomix_b200.topology`.
+
+Pinning: the reference ships no tests or golden vectors, so
+the pins are outputs of the *unmodified reference module* imported from
+``/root/reference`` in the build container by ``tests/golden/make_golden.py`` and
+committed under ``tests/golden/``; ``tests/test_oracle.py`` checks this file (and
+the plain-C restatement ``unet_ref.c``) against them.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module.
+
+``engine_rounding=True`` reproduces where the B200 engine rounds to bf16
+(packed weights, stored activations) while accumulating in fp32, which gives the
+tight parity gate of SURVEY.md section 8(c).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+DEFAULTS = dict(ngf=24, norm="batch", final_act="none", activation="relu",
+                pad_type="reflect", doubleconv=True, residual_connection=False,
+                pooling="Max", interp="nearest", use_skip_connection=True,
+                norm_eps=1e-5)
+
+
+def layer_program(input_nc, output_nc, num_downs, ngf, norm, activation,
+                  final_act, doubleconv, use_skip_connection):
+    """List of (op, index, cin, cout) in Sequential order + skip index lists.
+
+    Follows the constructor top to bottom: stem (network.py:309-326), encoder
+    loop (:334-369), bottleneck (:372-400), decoder loop (:403-445), final conv
+    (:450-464)."""
+    prog, enc_idx, dec_idx = [], [], []
+    has_n, has_a = norm != "none", activation != "none"
+
+    def block(ci, co):
+        prog.append(("conv", len(prog), ci, co))
+        if has_n:
+            prog.append(("norm", len(prog), co, co))
+        if has_a:
+            prog.append(("act", len(prog), co, co))
+
+    block(input_nc, ngf)
+    ch = ngf
+    for i in range(num_downs):
+        mult = 1 if i == 0 else 2
+        block(ch, ch * mult)
+        if doubleconv:
+            block(ch * mult, ch * mult)
+        enc_idx.append(len(prog) - 1)
+        prog.append(("pool", len(prog), ch * mult, ch * mult))
+        ch *= mult
+    block(ch, ch * 2)
+    if doubleconv:
+        block(ch * 2, ch * 2)
+    mult = 2 ** num_downs
+    for i in range(num_downs):
+        dec_idx.append(len(prog))
+        prog.append(("up", len(prog), ngf * mult, ngf * mult))
+        m = mult + mult // 2 if use_skip_connection else mult
+        block(ngf * m, ngf * (mult // 2))
+        if doubleconv:
+            block(ngf * (mult // 2), ngf * (mult // 2))
+        mult //= 2
+    prog.append(("conv", len(prog), ngf * mult, output_nc))
+    if final_act != "none":
+        prog.append(("final_act", len(prog), output_nc, output_nc))
+    return prog, enc_idx, dec_idx
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _activate(x, kind):
+    if kind == "relu":
+        return F.relu(x)                       # network.py:188-189
+    if kind == "lrelu":
+        return F.leaky_relu(x, 0.3)            # network.py:190-191 (slope 0.3)
+    if kind == "elu":
+        return F.elu(x)
+    if kind == "selu":
+        return F.selu(x)
+    if kind == "tanh":
+        return torch.tanh(x)
+    raise ValueError(kind)
+
+
+def conv3d_reflect(x, w, b):
+    """``nn.Conv3d(k=3, s=1, padding='same', padding_mode='reflect')``
+    (network.py:310-318): reflect-pad one voxel per side, valid correlation."""
+    return F.conv3d(F.pad(x, (1, 1, 1, 1, 1, 1), mode="reflect"), w, b)
+
+
+@torch.no_grad()
+def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False):
+    """Forward of ``Unet(**cfg)`` holding ``state`` (a state dict) on input ``x``
+    ``[N, input_nc, D, H, W]`` fp32.  Returns the output, or ``(output, taps)``
+    when ``layers`` (module indices) is non-empty (network.py:475-529)."""
+    c = dict(DEFAULTS)
+    c.update(cfg)
+    assert c["dimension"] == 3 and c["pad_type"] == "reflect"
+    assert not c["residual_connection"]
+    prog, enc_idx, dec_idx = layer_program(
+        c["input_nc"], c["output_nc"], c["num_downs"], c["ngf"], c["norm"],
+        c["activation"], c["final_act"], c["doubleconv"], c["use_skip_connection"])
+    g = lambda k: torch.as_tensor(state[k]).to(torch.float32)
+    feat, skips, taps = x.to(torch.float32), [], []
+    eps = c["norm_eps"]
+    n_conv = 0
+    for pos, (op, idx, ci, co) in enumerate(prog):
+        if op == "conv":
+            w = g(f"model.{idx}.weight")
+            b = g(f"model.{idx}.bias") if c["norm"] == "instance" else None   # :292
+            nxt = prog[pos + 1][0] if pos + 1 < len(prog) else ""
+            if engine_rounding:
+                # engine folds eval-BN into the packed weights before rounding
+                if nxt == "norm" and c["norm"] == "batch" and not training:
+                    s = g(f"model.{idx+1}.weight") / torch.sqrt(g(f"model.{idx+1}.running_var") + eps)
+                    w = w * s.view(-1, 1, 1, 1, 1)
+                    b = g(f"model.{idx+1}.bias") - g(f"model.{idx+1}.running_mean") * s
+                if n_conv > 0:                       # stem conv stays fp32
+                    w = _bf16(w)
+            feat = conv3d_reflect(feat, w, b)
+            n_conv += 1
+        elif op == "norm":
+            if c["norm"] == "batch":                 # network.py:154-155
+                if engine_rounding and not training:
+                    pass                             # already folded
+                else:
+                    feat = F.batch_norm(
+                        feat, g(f"model.{idx}.running_mean").clone(),
+                        g(f"model.{idx}.running_var").clone(),
+                        g(f"model.{idx}.weight"), g(f"model.{idx}.bias"),
+                        training=training, momentum=0.1, eps=eps)
+            elif c["norm"] == "instance":            # network.py:157-158
+                feat = F.instance_norm(feat, eps=eps)
+            elif c["norm"] == "instance_affine":
+                feat = F.instance_norm(feat, weight=g(f"model.{idx}.weight"),
+                                       bias=g(f"model.{idx}.bias"), eps=eps)
+        elif op == "act":
+            feat = _activate(feat, c["activation"])
+            if engine_rounding:
+                feat = _bf16(feat)                   # activations live in HBM as bf16
+        elif op == "final_act":
+            feat = _activate(feat, c["final_act"])
+        elif op == "pool":                           # network.py:297,368
+            feat = (F.max_pool3d if c["pooling"] == "Max" else F.avg_pool3d)(feat, 2)
+            if engine_rounding:
+                feat = _bf16(feat)
+        elif op == "up":                             # network.py:407
+            if c["interp"] == "nearest":
+                feat = F.interpolate(feat, scale_factor=2, mode="nearest")
+            else:
+                feat = F.interpolate(feat, scale_factor=2, mode=c["interp"])
+                if engine_rounding:
+                    feat = _bf16(feat)
+        if c["use_skip_connection"]:                 # network.py:543-547
+            if idx in dec_idx:
+                feat = torch.cat((skips.pop(), feat), dim=1)
+            if idx in enc_idx:
+                skips.append(feat)
+        if idx in layers:
+            taps.append(feat.clone())
+    return (feat, taps) if len(layers) else feat
+
+
+def random_state(cfg, seed, randomize_norm=True):
+    """A seeded state dict with the reference's shapes (for cases where no real
+    checkpoint exists).  Conv weights ~ U(-k, k) with k = 1/sqrt(fan_in) like
+    torch's default init; BatchNorm statistics are made non-trivial so that the
+    eval-mode fold is actually exercised."""
+    c = dict(DEFAULTS)
+    c.update(cfg)
+    prog, _, _ = layer_program(
+        c["input_nc"], c["output_nc"], c["num_downs"], c["ngf"], c["norm"],
+        c["activation"], c["final_act"], c["doubleconv"], c["use_skip_connection"])
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for op, idx, ci, co in prog:
+        if op == "conv":
+            k = (3.0 / (ci * 27)) ** 0.5 * 1.6      # keeps activations O(1) through ReLU stacks
+            sd[f"model.{idx}.weight"] = (torch.rand(co, ci, 3, 3, 3, generator=gen) * 2 - 1) * k
+            if c["norm"] == "instance":
+                sd[f"model.{idx}.bias"] = (torch.rand(co, generator=gen) * 2 - 1) * 0.1
+        elif op == "norm" and c["norm"] == "batch":
+            if randomize_norm:
+                sd[f"model.{idx}.weight"] = 0.5 + torch.rand(co, generator=gen)
+                sd[f"model.{idx}.bias"] = torch.rand(co, generator=gen) - 0.5
+                sd[f"model.{idx}.running_mean"] = torch.rand(co, generator=gen) - 0.5
+                sd[f"model.{idx}.running_var"] = 0.5 + torch.rand(co, generator=gen)
+            else:
+                sd[f"model.{idx}.weight"] = torch.ones(co)
+                sd[f"model.{idx}.bias"] = torch.zeros(co)
+                sd[f"model.{idx}.running_mean"] = torch.zeros(co)
+                sd[f"model.{idx}.running_var"] = torch.ones(co)
+            sd[f"model.{idx}.num_batches_tracked"] = torch.tensor(0)
+        elif op == "norm" and c["norm"] == "instance_affine":
+            sd[f"model.{idx}.weight"] = 0.5 + torch.rand(co, generator=gen)
+            sd[f"model.{idx}.bias"] = torch.rand(co, generator=gen) - 0.5
+    return sd

@@ -1,0 +1,218 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle and the
+golden vectors minted from the reference.  Everything here needs a B200.
+
+Tolerances (floating point):
+  * LOOSE  engine (bf16 operands, fp32 accumulate) vs the fp32 oracle:
+           rel-L2 <= 3e-2 and per-voxel cosine >= 0.995.  For scale: the reference
+           itself under CPU bf16 autocast sits at rel-L2 1.8e-2 from its fp32 self.
+  * TIGHT  engine vs the oracle rounding to bf16 at the same points (weights after
+           BN folding, stored activations), fp32 accumulate: rel-L2 <= 4e-3.
+"""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CFG_6M, golden, min_cosine, rand_input, rel_l2
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOOSE_REL, LOOSE_COS, TIGHT_REL = 3e-2, 0.995, 4e-3
+
+
+def make_engine(cfg, state, flags=0):
+    from anatomix_b200.engine import Engine
+    eng = Engine(cfg, "cuda:0", flags=flags)
+    eng.load_state(state)
+    return eng
+
+
+def check_against_oracle(cfg, state, x, y_gpu, tight=True):
+    want = O.unet_forward(cfg, state, x)
+    got = y_gpu.float().cpu()
+    assert torch.isfinite(got).all()
+    r, c = rel_l2(got, want), min_cosine(got, want)
+    assert r <= LOOSE_REL and c >= LOOSE_COS, f"loose gate: rel-L2 {r:.3e}, min cosine {c:.5f}"
+    if tight:
+        emu = O.unet_forward(cfg, state, x, engine_rounding=True)
+        rt = rel_l2(got, emu)
+        assert rt <= TIGHT_REL, f"tight gate: rel-L2 {rt:.3e} vs bf16-emulating oracle"
+    return r, c
+
+
+def localize(eng_a, eng_b, shape):
+    """Per-buffer comparison of two engines' workspaces after a forward."""
+    n, _, d, h, w = shape
+    wa, wb = eng_a.workspace(n, d, h, w), eng_b.workspace(n, d, h, w)
+    lines = []
+    for i, (off, nb, lvl, grp) in enumerate(eng_a.buffer_table(n, d, h, w)):
+        a = wa[off:off + nb].view(torch.bfloat16).float()
+        b = wb[off:off + nb].view(torch.bfloat16).float()
+        finite = torch.isfinite(a) & torch.isfinite(b)
+        diff = (a - b)[finite].abs().max().item() if finite.any() else float("nan")
+        lines.append(f"buffer {i:2d} level {lvl} groups {grp:3d}: max|diff| {diff:.4g} "
+                     f"nonfinite {int((~finite).sum())}")
+    return "\n".join(lines)
+
+
+def test_primitive_selftest():
+    from anatomix_b200 import _lib
+    ok, report = _lib.selftest(0)
+    print(report)
+    assert ok, report
+
+
+def small_cfg(**kw):
+    cfg = dict(dimension=3, input_nc=1, output_nc=16, num_downs=2, ngf=16)
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 8, 16, 8), (2, 1, 16, 32, 24)])
+def test_simt_path_matches_oracle_small(shape):
+    """Layout, stem conv, pooling, upsample/concat and weight packing, with the
+    tensor cores out of the picture (debug conv kernel on the same packed weights)."""
+    from anatomix_b200 import _lib
+    cfg = small_cfg()
+    state = O.random_state(cfg, seed=11)
+    x = rand_input(shape, 3)
+    eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
+    y = eng.forward(x.cuda())
+    torch.cuda.synchronize()
+    check_against_oracle(cfg, state, x, y)
+
+
+@pytest.mark.parametrize("shape,cfgkw", [
+    ((1, 1, 8, 16, 8), {}),
+    ((2, 1, 16, 32, 24), {}),
+    ((1, 1, 16, 16, 16), dict(num_downs=3, ngf=32, output_nc=24)),
+    ((1, 1, 8, 8, 8), dict(num_downs=1, ngf=64, output_nc=5, pooling="Avg", interp="trilinear",
+                           activation="lrelu")),
+])
+def test_tensor_core_path_matches_simt_and_oracle_small(shape, cfgkw):
+    from anatomix_b200 import _lib
+    cfg = small_cfg(**cfgkw)
+    state = O.random_state(cfg, seed=5)
+    x = rand_input(shape, 9)
+    ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
+    eng = make_engine(cfg, state)
+    xs = x.cuda()
+    y_ref = ref_eng.forward(xs)
+    y = eng.forward(xs)
+    torch.cuda.synchronize()
+    r = rel_l2(y.cpu(), y_ref.cpu())
+    assert r < 2e-3, f"tensor-core vs CUDA-core conv: rel-L2 {r:.3e}\n" + localize(eng, ref_eng, shape)
+    check_against_oracle(cfg, state, x, y)
+
+
+def test_g1_smallest_legal_size(state_6m):
+    g = golden("g1_6m_32.npz")
+    x = rand_input((1, 1, 32, 32, 32), 0)
+    eng = make_engine(CFG_6M, state_6m)
+    y = eng.forward(x.cuda())
+    check_against_oracle(CFG_6M, state_6m, x, y)
+    got, want = y.cpu(), torch.from_numpy(g["out"])
+    assert rel_l2(got, want) <= LOOSE_REL and min_cosine(got, want) >= LOOSE_COS
+
+
+def test_g2_batch_noncubic(state_6m):
+    g = golden("g2_6m_2x32x48x32.npz")
+    x = rand_input((2, 1, 32, 48, 32), 1)
+    eng = make_engine(CFG_6M, state_6m)
+    y = eng.forward(x.cuda())
+    check_against_oracle(CFG_6M, state_6m, x, y)
+    assert rel_l2(y.cpu()[:, :, ::2, ::2, ::2], torch.from_numpy(g["out_s2"])) <= LOOSE_REL
+
+
+def test_odd_bottleneck_size_48(state_6m):
+    x = rand_input((1, 1, 48, 32, 48), 4)      # bottleneck 3 x 2 x 3: both mirrors hit voxel 1
+    eng = make_engine(CFG_6M, state_6m)
+    check_against_oracle(CFG_6M, state_6m, x, eng.forward(x.cuda()))
+
+
+def test_g3_headline_shape_against_golden(state_6m):
+    g = golden("g3_6m_128.npz")
+    x = rand_input((1, 1, 128, 128, 128), 0)
+    eng = make_engine(CFG_6M, state_6m)
+    y = eng.forward(x.cuda()).cpu()
+    check_against_oracle(CFG_6M, state_6m, x, y)
+    assert rel_l2(y[:, :, ::8, ::8, ::8], torch.from_numpy(g["out_s8"])) <= LOOSE_REL
+    assert abs(y.double().mean().item() - g["mom"][0]) < 2e-2
+    assert abs(y.double().std().item() - g["mom"][1]) < 2e-2
+
+
+def test_g6_structured_inputs(state_6m):
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = golden("g6_6m_structured.npz")
+    eng = make_engine(CFG_6M, state_6m)
+    for name, x in mg.structured_inputs().items():
+        y = eng.forward(x.cuda()).cpu()
+        want = torch.from_numpy(g[name])
+        r = rel_l2(y[:, :, ::2, ::2, ::2], want)
+        assert r <= LOOSE_REL, f"{name}: rel-L2 {r:.3e}"
+
+
+def test_full_batch_properties(state_6m):
+    """BASELINE config 2 size (8 x 128^3): determinism, per-sample independence
+    (eval-BN has no cross-sample coupling) and oracle parity of the first and
+    last sample."""
+    xs = [rand_input((1, 1, 128, 128, 128), s) for s in (0, 1)]
+    x = torch.cat([xs[0], xs[1], xs[0], xs[1], xs[1], xs[0], xs[0], xs[1]]).cuda()
+    eng = make_engine(CFG_6M, state_6m)
+    y1 = eng.forward(x).clone()
+    y2 = eng.forward(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2), "two runs on the same input differ"
+    assert torch.equal(y1[0], y1[2]) and torch.equal(y1[0], y1[5]) and torch.equal(y1[1], y1[7])
+    single = eng.forward(xs[1].cuda())
+    assert torch.equal(single[0], y1[1]), "batched and single-volume results differ"
+    check_against_oracle(CFG_6M, state_6m, xs[0], y1[0:1], tight=False)
+    check_against_oracle(CFG_6M, state_6m, xs[1], y1[7:8], tight=False)
+
+
+def test_module_routes_to_engine_and_back(state_6m):
+    from anatomix_b200 import Unet
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda()
+    x = rand_input((2, 1, 32, 32, 32), 2)
+    xc = x.cuda()
+    # train mode (the state load_from_hf returns): BatchNorm batch statistics -> stock torch path
+    assert "train mode" in m.engine_ineligible_reason(xc)
+    m.eval()
+    assert "autograd" in m.engine_ineligible_reason(xc)
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(xc) is None
+        y = m(xc)
+        check_against_oracle(CFG_6M, state_6m, x, y)
+        y_taps, taps = m(xc, layers=[8])          # tap path stays on torch
+        assert rel_l2(y.cpu(), y_taps.cpu()) <= LOOSE_REL
+        # finetuning mutates parameters in place: the packed weights must follow
+        m.model[65].weight.mul_(2.0)
+        y2 = m(xc)
+    assert rel_l2(y2.cpu(), 2 * y.cpu()) < 1e-2
+    assert list(m._anx_binding.engines) == [torch.device("cuda", 0)]
+
+
+def test_errors_mirror_the_reference(state_6m):
+    from anatomix_b200.engine import Engine, EngineError
+    eng = make_engine(CFG_6M, state_6m)
+    for bad in [(1, 1, 16, 32, 32), (1, 1, 72, 32, 32)]:
+        with pytest.raises(ValueError):
+            eng.forward(torch.zeros(*bad, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(1, 2, 32, 32, 32, device="cuda"))
+    fresh = Engine(CFG_6M, "cuda:0")
+    with pytest.raises(EngineError) as ei:
+        fresh.forward(torch.zeros(1, 1, 32, 32, 32, device="cuda"))
+    assert "NOT_READY" in str(ei.value)
+    with pytest.raises(EngineError):
+        Engine(dict(CFG_6M, ngf=24), "cuda:0")   # widths the tensor-core tiles cannot take
