@@ -97,17 +97,25 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                 for (int c = 0; c < g.cin_chunks; ++c) {
                     const uint32_t sa = ka % g.a_stages;
                     mbar_wait(&bars->empty_a[sa], ((ka / g.a_stages) & 1) ^ 1, 1);
-                    mbar_arrive_expect_tx(&bars->full_a[sa], g.a_stage_bytes);
-                    tma_load_4d(a_ring + (size_t)sa * g.a_stage_bytes, &tmap_in, &bars->full_a[sa], t.x0 * 8, t.y0,
-                                t.z0, t.n * g.in_groups_total + g.in_group_offset + 2 * c);
+                    if (g.ablate & 4) {
+                        mbar_arrive(&bars->full_a[sa]);
+                    } else {
+                        mbar_arrive_expect_tx(&bars->full_a[sa], g.a_stage_bytes);
+                        tma_load_4d(a_ring + (size_t)sa * g.a_stage_bytes, &tmap_in, &bars->full_a[sa], t.x0 * 8,
+                                    t.y0, t.z0, t.n * g.in_groups_total + g.in_group_offset + 2 * c);
+                    }
                     ++ka;
                     for (int grp = 0; grp < g.groups; ++grp) {
                         const uint32_t sb = kb % g.b_stages;
                         mbar_wait(&bars->empty_b[sb], ((kb / g.b_stages) & 1) ^ 1, 2);
-                        mbar_arrive_expect_tx(&bars->full_b[sb], g.b_stage_bytes);
-                        bulk_load_1d(b_ring + (size_t)sb * g.b_stage_bytes,
-                                     wpack + (size_t)(c * g.groups + grp) * g.b_stage_bytes, g.b_stage_bytes,
-                                     &bars->full_b[sb]);
+                        if (g.ablate & 8) {
+                            mbar_arrive(&bars->full_b[sb]);
+                        } else {
+                            mbar_arrive_expect_tx(&bars->full_b[sb], g.b_stage_bytes);
+                            bulk_load_1d(b_ring + (size_t)sb * g.b_stage_bytes,
+                                         wpack + (size_t)(c * g.groups + grp) * g.b_stage_bytes, g.b_stage_bytes,
+                                         &bars->full_b[sb]);
+                        }
                         ++kb;
                     }
                 }
@@ -133,7 +141,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         mbar_wait(&bars->full_b[sb], (kb / g.b_stages) & 1, 5);
                         tc_fence_after();
                         const uint32_t b0 = smem_u32(b_ring + (size_t)sb * g.b_stage_bytes);
-                        if (g.fold) {
+                        if (g.ablate & 1) {
+                        } else if (g.fold) {
                             for (int j = 0; j < g.bz + 2; ++j) {
                                 const int lo = j - 2 > 0 ? j - 2 : 0;
                                 const int hi = j < g.bz - 1 ? j : g.bz - 1;
@@ -201,7 +210,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                 for (int cb = 0; cb < g.ncols / 16; ++cb) {
                     float v[16];
                     tmem_ld16(acc + b * g.ncols + cb * 16, v);
-                    if (in_xy && z < g.D) epilogue_store16(ep, t.n, z, y, x, cb, v);
+                    if (in_xy && z < g.D && !(g.ablate & 2)) epilogue_store16(ep, t.n, z, y, x, cb, v);
                 }
             }
             for (int col = 0; col < acc_cols; col += 16) tmem_st16_zero(acc + col);

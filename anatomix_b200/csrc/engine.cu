@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -253,6 +254,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     size_t left = budget - (size_t)g.a_stages * g.a_stage_bytes;
     g.b_stages = (int)std::min<size_t>(MAX_B_STAGES, left / g.b_stage_bytes);
     g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
+    if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
     g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
                               sizeof(UmmaBarriers));
     return g;

@@ -78,6 +78,7 @@ struct ConvGeom {
     uint32_t b_stage_bytes; // 9 * 32 * R, R = rows per tap matrix
     uint32_t b_rows;        // R = fold ? 3*ncols : ncols
     uint32_t smem_bytes;
+    uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load
 };
 
 }   // namespace anx

@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Headline benchmark: volumes/s of the anatomix 6M U-Net forward on 128^3 volumes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one forward of the engine over one batch of synthetic volumes
+(BASELINE.json configs[1]: 6M U-Net, batch 8 x 1 x 128^3, bf16 operands / fp32
+accumulate, fp32 in and out).  With N > 1 (launched by torchrun, one rank per
+GPU) every rank runs its own batch (weak scaling, no data-path collective in the
+timed value; the optional NCCL feature all-gather is timed separately and
+reported under "allgather").  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's own CPU path for the same metric: the
+reference is pure Python over torch ATen, so the arm runs the oracle's
+torch-functional port (same ATen operators, all host threads), one 128^3 volume
+per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG_6M = dict(dimension=3, input_nc=1, output_nc=16, num_downs=4, ngf=16)
+VOL = 128
+BATCH = 8
+CONV_GFLOP_PER_VOL = 346.986          # sum 2*27*Cin*Cout*DHW, SURVEY.md appendix A
+ALGO_MB_PER_VOL = 1025.0              # fused-minimum HBM bytes, SURVEY.md section 8(d)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def weights():
+    """Real released 6M weights when the fixture is present, else seeded random."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "anatomix_6m_state.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return {k: torch.from_numpy(z[k]) for k in z.files}, "anatomix.pth (released 6M weights)"
+    from oracle.unet_oracle import random_state
+    return random_state(CFG_6M, 0), "seeded random weights"
+
+
+def synth(n, seed):
+    return torch.rand(n, 1, VOL, VOL, VOL, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_port_time(steps, warmup, state):
+    """Seconds per 128^3 volume of the reference's CPU path (oracle port)."""
+    from oracle.unet_oracle import unet_forward
+    x = synth(1, 0)
+    for _ in range(warmup):
+        unet_forward(CFG_6M, state, x)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        unet_forward(CFG_6M, state, x)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    state, wsrc = weights()
+    ts = cpu_port_time(args.steps, max(1, min(args.warmup, 2)), state)
+    total = sum(ts)
+    v = len(ts) / total
+    line = {
+        "impl": "reference", "metric": "volumes/sec (128^3 1->16ch UNet forward)", "value": v, "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "anatomix 6M UNet forward, 1x(1,128,128,128) fp32 per step on the host CPU "
+                               "(reference PyTorch ATen path, oracle port)", "weights": wsrc},
+        "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{len(ts)} single-volume forwards of the same network and input size"},
+        "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from anatomix_b200.engine import Engine
+    state, wsrc = weights()
+    eng = Engine(CFG_6M, dev)
+    eng.load_state(state)
+    B = args.batch
+    peaks = load_peaks()
+
+    # inputs: rotate over enough distinct batches that their bytes exceed the 126 MB L2
+    n_in = 3
+    xs = [synth(B, 100 * rank + i).to(dev) for i in range(n_in)]
+    out = torch.empty((B, 16, VOL, VOL, VOL), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        eng.forward(xs[i % n_in], out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        eng.forward(xs[i % n_in], out=out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+
+    # end to end through the host-buffer C-ABI call: pinned input -> H2D -> forward -> D2H
+    x_host = [synth(B, 7 + i).pin_memory() for i in range(2)]
+    y_host = torch.empty((B, 16, VOL, VOL, VOL), dtype=torch.float32).pin_memory()
+    dev_in = torch.empty((B, 1, VOL, VOL, VOL), dtype=torch.float32, device=dev)
+    e2e_steps = max(3, min(args.steps, 10))
+    eng.forward_host(x_host[0], y_host, dev_in, out)
+    barrier()
+    ev0.record()
+    for i in range(e2e_steps):
+        eng.forward_host(x_host[i % 2], y_host, dev_in, out)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+
+    # per-launch device times (CUDA events around every launch of one forward), averaged
+    reps, acc = 5, {}
+    order = []
+    for r in range(reps):
+        for name, t in eng.profile(xs[r % n_in]):
+            if name not in acc:
+                acc[name] = 0.0
+                order.append(name)
+            acc[name] += t / reps
+    conv_ms = sum(t for n, t in acc.items() if n.startswith("conv") and not n.startswith("conv0_"))
+    fwd_ms = sum(acc.values())
+
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = times.tolist()
+
+    allgather = None
+    if world > 1:
+        gathered = torch.empty((world * B, 16, VOL, VOL, VOL), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, out)
+        barrier()
+        ev0.record()
+        for _ in range(3):
+            dist.all_gather_into_tensor(gathered, out)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allgather = {"ms": t.item(), "bytes_per_rank": out.numel() * 4,
+                     "volumes_per_s_with_gather": world * B / ((ms / args.steps + t.item()) / 1e3)}
+
+    if rank == 0:
+        vols = world * B * args.steps
+        value = vols / (ms / 1e3)
+        # stem conv (CUDA cores) excluded from the tensor-core roofline: 1.81 GFLOP of 346.99
+        tc_flops = (CONV_GFLOP_PER_VOL - 1.812) * 1e9 * B
+        achieved = tc_flops / (conv_ms / 1e3) / 1e12
+        line = {
+            "metric": "volumes/sec (128^3 1->16ch UNet forward)", "value": value, "unit": "volumes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"anatomix 6M UNet, batch {B}x128^3 bf16 on 1xB200 per rank (BASELINE configs[1])",
+                       "weights": wsrc, "l2": f"{n_in} distinct input batches rotated; activations per step "
+                       f"({eng.workspace_bytes(B, VOL, VOL, VOL) >> 20} MiB) exceed the 126 MB L2",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective in the timed value"},
+            "e2e": {"value": world * B * e2e_steps / (ms_e2e / 1e3), "unit": "volumes/s",
+                    "h2d_bytes_per_step": B * VOL ** 3 * 4, "d2h_bytes_per_step": B * 16 * VOL ** 3 * 4},
+            "gpu_launches": eng.launches_per_forward(B, VOL, VOL, VOL) * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv3_umma_kernel (19 launches per forward)",
+                         "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained)",
+                         "traffic": None,
+                         "whole_forward": {"ms_sum_of_launches": fwd_ms,
+                                           "hbm_gbs_algorithmic": ALGO_MB_PER_VOL * 1e6 * B / (fwd_ms / 1e3) / 1e9,
+                                           "hbm_peak": peaks["hbm"],
+                                           "ceiling_vol_s": 4068.0, "frac_of_ceiling": value / world / 4068.0}},
+            "launch_ms": {n: round(acc[n], 4) for n in order},
+        }
+        if allgather:
+            line["allgather"] = allgather
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count())
+            ts = cpu_port_time(4, 1, state)
+            line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "volumes/s",
+                                    "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "4 single-volume 128^3 forwards (1 warm-up) of the oracle's "
+                                              "torch-ATen port of the reference CPU path"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
