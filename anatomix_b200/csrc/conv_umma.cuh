@@ -20,30 +20,34 @@
 // ONE instruction with N = 3*ncols and B = [W(+1) | W(0) | W(-1)] stacked along N,
 // targeted at column (j-2)*ncols, accumulates all three at once.  That cuts the
 // shared-memory reads of A (the bottleneck for thin layers: a 4 KB A tile feeds
-// only N columns) by 3x.  Accumulators are zeroed by the epilogue warps after
-// they drain them, so every MMA accumulates and the overlap needs no special
-// first-touch case.
+// only N columns) by 3x.  The epilogue warps re-initialise the accumulators with
+// the per-channel shift (folded BatchNorm / conv bias) right after draining them,
+// so every MMA accumulates, the overlap needs no first-touch case and the
+// epilogue needs no bias add.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM
-// allocator + MMA issuer (1 lane), warps 2..5 = epilogue (TMEM lane quadrant =
-// warp_id % 4).  Rings: A bricks (stage = chunk), B weight slabs (stage = chunk
-// x dz-group), TMEM accumulator stages.  Persistent CTAs stride over tiles.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (warp-uniform loop, one elected lane issues), warps 2..9 = epilogue (TMEM
+// lane quadrant = warp_id % 4, the two warps of a quadrant take alternate output
+// planes).  Rings: A bricks (stage = chunk), B weight slabs (stage = chunk x
+// dz-group), TMEM accumulator stages.  Persistent CTAs stride over tiles.
 #pragma once
 #include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace anx {
 
-constexpr int UMMA_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int UMMA_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 
-struct UmmaBarriers {
+struct UmmaShared {          // lives behind the A / B rings in dynamic shared memory
     uint64_t full_a[MAX_A_STAGES], empty_a[MAX_A_STAGES];
     uint64_t full_b[MAX_B_STAGES], empty_b[MAX_B_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_slot;
-    uint32_t pad;
+    uint32_t pad[3];
+    float shift[256];        // per-channel accumulator seed (folded BN shift / bias)
 };
 
 struct TileCoord { int n, z0, y0, x0; };
@@ -60,33 +64,38 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom &g, int tile) {
     return t;
 }
 
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) {
+    return ((uint64_t)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g, const uint8_t *__restrict__ wpack,
                   const Epilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_ring = smem;
     uint8_t *b_ring = a_ring + (size_t)g.a_stages * g.a_stage_bytes;
-    UmmaBarriers *bars = reinterpret_cast<UmmaBarriers *>(b_ring + (size_t)g.b_stages * g.b_stage_bytes);
+    UmmaShared *sh = reinterpret_cast<UmmaShared *>(b_ring + (size_t)g.b_stages * g.b_stage_bytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int acc_cols = g.bz * g.ncols;   // TMEM columns per accumulator stage
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < g.a_stages; ++i) { mbar_init(&bars->full_a[i], 1); mbar_init(&bars->empty_a[i], 1); }
-        for (int i = 0; i < g.b_stages; ++i) { mbar_init(&bars->full_b[i], 1); mbar_init(&bars->empty_b[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 128); }
+        for (int i = 0; i < g.a_stages; ++i) { mbar_init(&sh->full_a[i], 1); mbar_init(&sh->empty_a[i], 1); }
+        for (int i = 0; i < g.b_stages; ++i) { mbar_init(&sh->full_b[i], 1); mbar_init(&sh->empty_b[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sh->tmem_full[i], 1); mbar_init(&sh->tmem_empty[i], 32 * EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_in);
     }
     if (warp == 1) {
-        tmem_alloc_dyn(&bars->tmem_slot, (uint32_t)g.tmem_cols);
+        tmem_alloc_dyn(&sh->tmem_slot, (uint32_t)g.tmem_cols);
         tmem_relinquish();
     }
+    for (int i = threadIdx.x; i < g.ncols; i += blockDim.x) sh->shift[i] = ep.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_slot;
+    const uint32_t tmem_base = sh->tmem_slot;
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
@@ -96,25 +105,25 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                 const TileCoord t = decode_tile(g, tile);
                 for (int c = 0; c < g.cin_chunks; ++c) {
                     const uint32_t sa = ka % g.a_stages;
-                    mbar_wait(&bars->empty_a[sa], ((ka / g.a_stages) & 1) ^ 1, 1);
+                    mbar_wait(&sh->empty_a[sa], ((ka / g.a_stages) & 1) ^ 1, 1);
                     if (g.ablate & 4) {
-                        mbar_arrive(&bars->full_a[sa]);
+                        mbar_arrive(&sh->full_a[sa]);
                     } else {
-                        mbar_arrive_expect_tx(&bars->full_a[sa], g.a_stage_bytes);
-                        tma_load_4d(a_ring + (size_t)sa * g.a_stage_bytes, &tmap_in, &bars->full_a[sa], t.x0 * 8,
+                        mbar_arrive_expect_tx(&sh->full_a[sa], g.a_stage_bytes);
+                        tma_load_4d(a_ring + (size_t)sa * g.a_stage_bytes, &tmap_in, &sh->full_a[sa], t.x0 * 8,
                                     t.y0, t.z0, t.n * g.in_groups_total + g.in_group_offset + 2 * c);
                     }
                     ++ka;
                     for (int grp = 0; grp < g.groups; ++grp) {
                         const uint32_t sb = kb % g.b_stages;
-                        mbar_wait(&bars->empty_b[sb], ((kb / g.b_stages) & 1) ^ 1, 2);
+                        mbar_wait(&sh->empty_b[sb], ((kb / g.b_stages) & 1) ^ 1, 2);
                         if (g.ablate & 8) {
-                            mbar_arrive(&bars->full_b[sb]);
+                            mbar_arrive(&sh->full_b[sb]);
                         } else {
-                            mbar_arrive_expect_tx(&bars->full_b[sb], g.b_stage_bytes);
+                            mbar_arrive_expect_tx(&sh->full_b[sb], g.b_stage_bytes);
                             bulk_load_1d(b_ring + (size_t)sb * g.b_stage_bytes,
                                          wpack + (size_t)(c * g.groups + grp) * g.b_stage_bytes, g.b_stage_bytes,
-                                         &bars->full_b[sb]);
+                                         &sh->full_b[sb]);
                         }
                         ++kb;
                     }
@@ -123,100 +132,132 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ---------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            uint32_t ka = 0, kb = 0, it = 0;
-            const uint32_t R = g.b_rows;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % g.acc_stages;
-                mbar_wait(&bars->tmem_empty[s], (it / g.acc_stages) & 1, 3);
-                tc_fence_after();
-                const uint32_t acc = tmem_base + s * acc_cols;
-                for (int c = 0; c < g.cin_chunks; ++c) {
-                    const uint32_t sa = ka % g.a_stages;
-                    mbar_wait(&bars->full_a[sa], (ka / g.a_stages) & 1, 4);
-                    const uint32_t a0 = smem_u32(a_ring + (size_t)sa * g.a_stage_bytes);
-                    for (int grp = 0; grp < g.groups; ++grp) {
-                        const uint32_t sb = kb % g.b_stages;
-                        mbar_wait(&bars->full_b[sb], (kb / g.b_stages) & 1, 5);
-                        tc_fence_after();
-                        const uint32_t b0 = smem_u32(b_ring + (size_t)sb * g.b_stage_bytes);
-                        if (g.ablate & 1) {
-                        } else if (g.fold) {
-                            for (int j = 0; j < g.bz + 2; ++j) {
-                                const int lo = j - 2 > 0 ? j - 2 : 0;
-                                const int hi = j < g.bz - 1 ? j : g.bz - 1;
-                                const uint32_t n_mma = (uint32_t)(hi - lo + 1) * g.ncols;
-                                const uint32_t row0 = (uint32_t)(lo - (j - 2)) * g.ncols;
-                                const uint32_t idesc = idesc_bf16_m128(n_mma);
-                                const uint32_t dcol = acc + lo * g.ncols;
+        // ---------------------------------------------- MMA issuer (warp-uniform)
+        uint32_t ka = 0, kb = 0, it = 0;
+        const uint32_t R = g.b_rows;
+        const uint32_t a_hi = (ROW_BYTES >> 4) | (1u << 14);     // SBO = 160 B, descriptor version 1
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B
+        const uint32_t a_lbo_bits = ((g.a_lbo >> 4) & 0x3FFF) << 16;
+        const uint32_t b_lbo_bits = (R & 0x3FFF) << 16;          // LBO = 16 * R bytes
+        const uint32_t b_tap = 2 * R;                            // 32 * R bytes per tap, in 16 B units
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % g.acc_stages;
+            mbar_wait(&sh->tmem_empty[s], (it / g.acc_stages) & 1, 3);
+            tc_fence_after();
+            const uint32_t acc = tmem_u + s * acc_cols;
+            for (int c = 0; c < g.cin_chunks; ++c) {
+                const uint32_t sa = ka % g.a_stages;
+                mbar_wait(&sh->full_a[sa], (ka / g.a_stages) & 1, 4);
+                const uint32_t a_lo = ((smem_u32(a_ring + (size_t)sa * g.a_stage_bytes) & 0x3FFFF) >> 4) | a_lbo_bits;
+                for (int grp = 0; grp < g.groups; ++grp) {
+                    const uint32_t sb = kb % g.b_stages;
+                    mbar_wait(&sh->full_b[sb], (kb / g.b_stages) & 1, 5);
+                    tc_fence_after();
+                    const uint32_t b_lo = ((smem_u32(b_ring + (size_t)sb * g.b_stage_bytes) & 0x3FFFF) >> 4) | b_lbo_bits;
+                    if (g.ablate & 1) {
+                    } else if (g.fold) {
+                        for (int j = 0; j < g.bz + 2; ++j) {
+                            const int lo = j - 2 > 0 ? j - 2 : 0;
+                            const int hi = j < g.bz - 1 ? j : g.bz - 1;
+                            const uint32_t idesc = idesc_bf16_m128((uint32_t)(hi - lo + 1) * g.ncols);
+                            const uint32_t dcol = acc + lo * g.ncols;
+                            const uint32_t aj = a_lo + j * (HALO_Y * HALO_X);
+                            const uint32_t bj = b_lo + (uint32_t)(lo - (j - 2)) * g.ncols;   // first B row, 16 B each
 #pragma unroll
-                                for (int t = 0; t < 9; ++t) {
-                                    const int dy = t / 3, dx = t - dy * 3;
-                                    const uint64_t ad = smem_desc_kmajor_noswz(
-                                        a0 + ((j * HALO_Y + dy) * HALO_X + dx) * 16, g.a_lbo, ROW_BYTES);
-                                    const uint64_t bd =
-                                        smem_desc_kmajor_noswz(b0 + t * 32 * R + row0 * 16, 16 * R, 128);
-                                    umma_bf16(dcol, ad, bd, idesc, 1);
-                                }
-                            }
-                        } else {
-                            const uint32_t idesc = idesc_bf16_m128(g.ncols);
-                            for (int b = 0; b < g.bz; ++b) {
-                                const int j = b + grp;   // grp = kz = dz + 1
-                                const uint32_t dcol = acc + b * g.ncols;
-#pragma unroll
-                                for (int t = 0; t < 9; ++t) {
-                                    const int dy = t / 3, dx = t - dy * 3;
-                                    const uint64_t ad = smem_desc_kmajor_noswz(
-                                        a0 + ((j * HALO_Y + dy) * HALO_X + dx) * 16, g.a_lbo, ROW_BYTES);
-                                    const uint64_t bd = smem_desc_kmajor_noswz(b0 + t * 32 * R, 16 * R, 128);
-                                    umma_bf16(dcol, ad, bd, idesc, 1);
-                                }
-                            }
+                            for (int t = 0; t < 9; ++t)
+                                umma_bf16_warp(dcol, make_desc(a_hi, aj + (t / 3) * HALO_X + (t % 3)),
+                                               make_desc(b_hi, bj + t * b_tap), idesc);
                         }
-                        umma_commit(&bars->empty_b[sb]);
-                        ++kb;
+                    } else {
+                        const uint32_t idesc = idesc_bf16_m128(g.ncols);
+                        for (int b = 0; b < g.bz; ++b) {
+                            const uint32_t dcol = acc + b * g.ncols;
+                            const uint32_t aj = a_lo + (b + grp) * (HALO_Y * HALO_X);   // grp = kz = dz + 1
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+                                umma_bf16_warp(dcol, make_desc(a_hi, aj + (t / 3) * HALO_X + (t % 3)),
+                                               make_desc(b_hi, b_lo + t * b_tap), idesc);
+                        }
                     }
-                    umma_commit(&bars->empty_a[sa]);
-                    ++ka;
+                    umma_commit_warp(&sh->empty_b[sb]);
+                    ++kb;
                 }
-                umma_commit(&bars->tmem_full[s]);
+                umma_commit_warp(&sh->empty_a[sa]);
+                ++ka;
             }
+            umma_commit_warp(&sh->tmem_full[s]);
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;                    // TMEM lane quadrant this warp may touch
+        const int half = (warp - 2) >> 2;          // which of the quadrant's two warps: takes planes b = half (mod 2)
         const int r = q * 32 + lane;               // accumulator row = voxel within the 8x16 patch
         const int ly = r >> 3, lx = r & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int col = 0; col < g.acc_stages * acc_cols; col += 16) tmem_st16_zero(lane_base + col);
+        const int chunks = g.ncols >> 4;
+        // seed every accumulator stage with the per-channel shift
+        for (int s = 0; s < g.acc_stages; ++s)
+            for (int b = half; b < g.bz; b += 2)
+                for (int cb = 0; cb < chunks; ++cb) tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + cb * 16);
         tmem_wait_st();
         tc_fence_before();
-        for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&bars->tmem_empty[s]);
+        for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
 
+        const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
+        const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
+        const size_t gstride = (size_t)(Dd + 2) * plane;
+        const size_t vol = (size_t)Dd * Hh * Ww;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(g, tile);
             const uint32_t s = it % g.acc_stages;
-            mbar_wait(&bars->tmem_full[s], (it / g.acc_stages) & 1, 6);
-            tc_fence_after();
             const int y = t.y0 + ly, x = t.x0 + lx;
             const bool in_xy = (y < g.H) && (x < g.W);
+            const bool edge_xy = (x == 1) | (x == Ww - 2) | (y == 1) | (y == Hh - 2);
+            uint4 *pbase = nullptr;
+            float *fbase = nullptr;
+            if (ep.mode == OUT_PADDED_BF16)
+                pbase = ep.dst.at(t.n, 0, t.z0 + 1, y + 1, x + 1);
+            else
+                fbase = ep.out_f32 + (size_t)t.n * ep.cout * vol + ((size_t)t.z0 * Hh + y) * Ww + x;
+            mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
+            tc_fence_after();
             const uint32_t acc = lane_base + s * acc_cols;
-            for (int b = 0; b < g.bz; ++b) {
+            for (int b = half; b < g.bz; b += 2) {
                 const int z = t.z0 + b;
-                for (int cb = 0; cb < g.ncols / 16; ++cb) {
+                const bool ok = in_xy && z < g.D && !(g.ablate & 2);
+                for (int cb = 0; cb < chunks; ++cb) {
                     float v[16];
                     tmem_ld16(acc + b * g.ncols + cb * 16, v);
-                    if (in_xy && z < g.D && !(g.ablate & 2)) epilogue_store16(ep, t.n, z, y, x, cb, v);
+                    tmem_st16(acc + b * g.ncols + cb * 16, sh->shift + cb * 16);   // re-seed for the next tile
+                    if (!ok) continue;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
+                    const int c0 = cb * 16;
+                    if (ep.mode == OUT_PADDED_BF16) {
+                        const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
+                        if (ngroups <= 0) continue;
+                        const uint4 q0 = pack_bf16x8(v), q1 = pack_bf16x8(v + 8);
+                        if (!edge_xy && z != 1 && z != Dd - 2) {
+                            uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
+                            *p = q0;
+                            if (ngroups > 1) p[gstride] = q1;
+                        } else {
+                            store_padded_groups(ep.dst, t.n, 2 * cb, ngroups, z, y, x, q0, q1);
+                        }
+                    } else {
+                        float *o = fbase + (size_t)c0 * vol + (size_t)b * Hh * Ww;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                    }
                 }
             }
-            for (int col = 0; col < acc_cols; col += 16) tmem_st16_zero(acc + col);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&bars->tmem_empty[s]);
+            mbar_arrive(&sh->tmem_empty[s]);
         }
     }
 

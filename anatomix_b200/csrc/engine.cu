@@ -247,7 +247,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.a_stage_bytes = 2 * g.a_lbo;
     g.b_rows = c.fold ? 3 * c.ncols : c.ncols;
     g.b_stage_bytes = 9 * 32 * g.b_rows;
-    const size_t budget = (size_t)e->max_smem - sizeof(UmmaBarriers) - 1024;
+    const size_t budget = (size_t)e->max_smem - sizeof(UmmaShared) - 1024;
     g.a_stages = 3;
     g.b_stages = 2;
     while (g.a_stages > 1 && (size_t)g.a_stages * g.a_stage_bytes + 2u * g.b_stage_bytes > budget) --g.a_stages;
@@ -256,7 +256,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
     if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
     g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
-                              sizeof(UmmaBarriers));
+                              sizeof(UmmaShared));
     return g;
 }
 
@@ -469,7 +469,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
     build_program(e);
     for (auto &c : e->convs) {
-        c.fold = (!c.is_stem && 3 * c.ncols <= 256) ? 1 : 0;
+        c.fold = (!c.is_stem && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
     }
     cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);

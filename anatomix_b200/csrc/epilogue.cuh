@@ -25,34 +25,39 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 &q, float *v) {
 }
 
 // Padded-coordinate targets of interior coordinate v on an axis of size S:
-// always v+1; additionally the shell cell 0 when v == 1 and S+1 when v == S-2
-// (reflect: shell[0] = x[1], shell[S+1] = x[S-2]).
-__device__ __forceinline__ int mirror_targets(int v, int S, int *t) {
-    int n = 0;
-    t[n++] = v + 1;
-    if (v == 1) t[n++] = 0;
-    if (v == S - 2) t[n++] = S + 1;
-    return n;
+// always v+1 (k = 0); additionally the shell cell 0 when v == 1 (k = 1) and S+1
+// when v == S-2 (k = 2) (reflect: shell[0] = x[1], shell[S+1] = x[S-2]).  -1 = none.
+__device__ __forceinline__ int mirror_target(int v, int S, int k) {
+    if (k == 0) return v + 1;
+    if (k == 1) return v == 1 ? 0 : -1;
+    return v == S - 2 ? S + 1 : -1;
 }
 
 // Stores `ngroups` (1 or 2) packed 8-channel groups of voxel (n,z,y,x) starting at
 // group g0 into a padded planar buffer, including its reflect-shell copies.
 __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, int g0, int ngroups, int z, int y,
                                                     int x, const uint4 &q0, const uint4 &q1) {
-    int zt[3], yt[3], xt[3];
-    const int nz = mirror_targets(z, dst.D, zt), ny = mirror_targets(y, dst.H, yt), nx = mirror_targets(x, dst.W, xt);
-    if (nz + ny + nx == 3) {   // interior voxel: the common case
-        uint4 *p = dst.at(n, g0, zt[0], yt[0], xt[0]);
+    const bool interior = (z != 1) & (z != dst.D - 2) & (y != 1) & (y != dst.H - 2) & (x != 1) & (x != dst.W - 2);
+    if (interior) {   // the common case
+        uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
         *p = q0;
-        if (ngroups > 1) *dst.at(n, g0 + 1, zt[0], yt[0], xt[0]) = q1;
+        if (ngroups > 1) *dst.at(n, g0 + 1, z + 1, y + 1, x + 1) = q1;
         return;
     }
-    for (int a = 0; a < nz; ++a)
-        for (int b = 0; b < ny; ++b)
-            for (int c = 0; c < nx; ++c) {
-                *dst.at(n, g0, zt[a], yt[b], xt[c]) = q0;
-                if (ngroups > 1) *dst.at(n, g0 + 1, zt[a], yt[b], xt[c]) = q1;
+    for (int a = 0; a < 3; ++a) {
+        const int zt = mirror_target(z, dst.D, a);
+        if (zt < 0) continue;
+        for (int b = 0; b < 3; ++b) {
+            const int yt = mirror_target(y, dst.H, b);
+            if (yt < 0) continue;
+            for (int c = 0; c < 3; ++c) {
+                const int xt = mirror_target(x, dst.W, c);
+                if (xt < 0) continue;
+                *dst.at(n, g0, zt, yt, xt) = q0;
+                if (ngroups > 1) *dst.at(n, g0 + 1, zt, yt, xt) = q1;
             }
+        }
+    }
 }
 
 __device__ __forceinline__ float activate(float v, int act, float slope) {

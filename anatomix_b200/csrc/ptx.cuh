@@ -109,6 +109,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, executed by a whole converged warp with warp-uniform operands: one elected
+// lane issues.  Keeping the surrounding loop warp-uniform lets ptxas hold the
+// descriptors in uniform registers instead of wrapping every MMA in a
+// per-thread election loop (R2UR + ELECT + BRA.U.ANY).
+__device__ __forceinline__ void umma_bf16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.b32 pa, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
 // All previously issued tcgen05 async ops of this thread arrive on `bar` when done.
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -143,6 +164,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 columns of this thread's lane <- v[0..15]
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+          "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+          "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+// issue only; pair with tmem_wait_ld() before reading v
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
     uint32_t z = 0;
     asm volatile(
