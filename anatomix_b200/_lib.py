@@ -19,6 +19,8 @@ ACT = {"none": 0, "relu": 1, "lrelu": 2}
 POOL = {"Max": 0, "Avg": 1}
 INTERP = {"nearest": 0, "trilinear": 1}
 FLAG_FORCE_SIMT = 1
+FLAG_STORE_FP16 = 2
+FLAG_STORE_BF16 = 4
 
 # every symbol include/anatomix_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -47,12 +47,14 @@ struct UmmaShared {          // lives behind the A / B rings in dynamic shared m
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_slot;
     uint32_t pad[3];
-    float shift[256];        // per-channel accumulator seed (folded BN shift / bias)
+    float shift[1024];       // per-channel accumulator seed (folded BN shift / bias), all splits
 };
 
-struct TileCoord { int n, z0, y0, x0; };
+struct TileCoord { int n, z0, y0, x0, split; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvGeom &g, int tile) {
     TileCoord t;
+    t.split = tile % g.n_splits;       // consecutive CTAs share one brick and take different channel splits
+    tile /= g.n_splits;
     t.n = tile / g.tiles_per_sample;
     int r = tile - t.n * g.tiles_per_sample;
     int tz = r / (g.tiles_y * g.tiles_x);
@@ -76,7 +78,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
     uint8_t *b_ring = a_ring + (size_t)g.a_stages * g.a_stage_bytes;
     UmmaShared *sh = reinterpret_cast<UmmaShared *>(b_ring + (size_t)g.b_stages * g.b_stage_bytes);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int acc_cols = g.bz * g.ncols;   // TMEM columns per accumulator stage
 
@@ -91,7 +93,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         tmem_alloc_dyn(&sh->tmem_slot, (uint32_t)g.tmem_cols);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < g.ncols; i += blockDim.x) sh->shift[i] = ep.bias[i];
+    for (int i = threadIdx.x; i < g.ncols * g.n_splits; i += blockDim.x) sh->shift[i] = ep.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -122,7 +124,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         } else {
                             mbar_arrive_expect_tx(&sh->full_b[sb], g.b_stage_bytes);
                             bulk_load_1d(b_ring + (size_t)sb * g.b_stage_bytes,
-                                         wpack + (size_t)(c * g.groups + grp) * g.b_stage_bytes, g.b_stage_bytes,
+                                         wpack + ((size_t)(t.split * g.cin_chunks + c) * g.groups + grp) * g.b_stage_bytes,
+                                         g.b_stage_bytes,
                                          &sh->full_b[sb]);
                         }
                         ++kb;
@@ -143,16 +146,16 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it % g.acc_stages;
-            mbar_wait(&sh->tmem_empty[s], (it / g.acc_stages) & 1, 3);
+            mbar_wait_warp(&sh->tmem_empty[s], (it / g.acc_stages) & 1, 3);
             tc_fence_after();
             const uint32_t acc = tmem_u + s * acc_cols;
             for (int c = 0; c < g.cin_chunks; ++c) {
                 const uint32_t sa = ka % g.a_stages;
-                mbar_wait(&sh->full_a[sa], (ka / g.a_stages) & 1, 4);
+                mbar_wait_warp(&sh->full_a[sa], (ka / g.a_stages) & 1, 4);
                 const uint32_t a_lo = ((smem_u32(a_ring + (size_t)sa * g.a_stage_bytes) & 0x3FFFF) >> 4) | a_lbo_bits;
                 for (int grp = 0; grp < g.groups; ++grp) {
                     const uint32_t sb = kb % g.b_stages;
-                    mbar_wait(&sh->full_b[sb], (kb / g.b_stages) & 1, 5);
+                    mbar_wait_warp(&sh->full_b[sb], (kb / g.b_stages) & 1, 5);
                     tc_fence_after();
                     const uint32_t b_lo = ((smem_u32(b_ring + (size_t)sb * g.b_stage_bytes) & 0x3FFFF) >> 4) | b_lbo_bits;
                     if (g.ablate & 1) {
@@ -160,7 +163,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         for (int j = 0; j < g.bz + 2; ++j) {
                             const int lo = j - 2 > 0 ? j - 2 : 0;
                             const int hi = j < g.bz - 1 ? j : g.bz - 1;
-                            const uint32_t idesc = idesc_bf16_m128((uint32_t)(hi - lo + 1) * g.ncols);
+                            const uint32_t idesc = idesc_m128((uint32_t)(hi - lo + 1) * g.ncols, g.dt);
                             const uint32_t dcol = acc + lo * g.ncols;
                             const uint32_t aj = a_lo + j * (HALO_Y * HALO_X);
                             const uint32_t bj = b_lo + (uint32_t)(lo - (j - 2)) * g.ncols;   // first B row, 16 B each
@@ -170,7 +173,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                                                make_desc(b_hi, bj + t * b_tap), idesc);
                         }
                     } else {
-                        const uint32_t idesc = idesc_bf16_m128(g.ncols);
+                        const uint32_t idesc = idesc_m128(g.ncols, g.dt);
                         for (int b = 0; b < g.bz; ++b) {
                             const uint32_t dcol = acc + b * g.ncols;
                             const uint32_t aj = a_lo + (b + grp) * (HALO_Y * HALO_X);   // grp = kz = dz + 1
@@ -197,10 +200,13 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         const int ly = r >> 3, lx = r & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks = g.ncols >> 4;
-        // seed every accumulator stage with the per-channel shift
-        for (int s = 0; s < g.acc_stages; ++s)
+        // seed every accumulator stage with the per-channel shift of the tile that will use it
+        for (int s = 0; s < g.acc_stages; ++s) {
+            const int split = (blockIdx.x + s * (int)gridDim.x) % g.n_splits;
             for (int b = half; b < g.bz; b += 2)
-                for (int cb = 0; cb < chunks; ++cb) tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + cb * 16);
+                for (int cb = 0; cb < chunks; ++cb)
+                    tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + split * g.ncols + cb * 16);
+        }
         tmem_wait_st();
         tc_fence_before();
         for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
@@ -213,46 +219,63 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(g, tile);
             const uint32_t s = it % g.acc_stages;
+            const int chan0 = t.split * g.ncols;
+            const int next_split = (tile + g.acc_stages * (int)gridDim.x) % g.n_splits;
+            const float *seed = sh->shift + next_split * g.ncols;
             const int y = t.y0 + ly, x = t.x0 + lx;
             const bool in_xy = (y < g.H) && (x < g.W);
             const bool edge_xy = (x == 1) | (x == Ww - 2) | (y == 1) | (y == Hh - 2);
             uint4 *pbase = nullptr;
             float *fbase = nullptr;
             if (ep.mode == OUT_PADDED_BF16)
-                pbase = ep.dst.at(t.n, 0, t.z0 + 1, y + 1, x + 1);
+                pbase = ep.dst.at(t.n, chan0 >> 3, t.z0 + 1, y + 1, x + 1);
             else
-                fbase = ep.out_f32 + (size_t)t.n * ep.cout * vol + ((size_t)t.z0 * Hh + y) * Ww + x;
+                fbase = ep.out_f32 + ((size_t)t.n * ep.cout + chan0) * vol + ((size_t)t.z0 * Hh + y) * Ww + x;
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
             tc_fence_after();
             const uint32_t acc = lane_base + s * acc_cols;
-            for (int b = half; b < g.bz; b += 2) {
-                const int z = t.z0 + b;
-                const bool ok = in_xy && z < g.D && !(g.ablate & 2);
-                for (int cb = 0; cb < chunks; ++cb) {
+            for (int cb = 0; cb < chunks; ++cb) {
+                const int c0 = chan0 + cb * 16;
+                float s16[16], q16[16];
+                if (ep.stats) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
+                }
+                for (int b = half; b < g.bz; b += 2) {
+                    const int z = t.z0 + b;
+                    const bool ok = in_xy && z < g.D && !(g.ablate & 2);
                     float v[16];
+                    __syncwarp();   // tcgen05.ld/st are warp-collective
                     tmem_ld16(acc + b * g.ncols + cb * 16, v);
-                    tmem_st16(acc + b * g.ncols + cb * 16, sh->shift + cb * 16);   // re-seed for the next tile
+                    tmem_st16(acc + b * g.ncols + cb * 16, seed + cb * 16);   // re-seed for the tile after next
+                    if (ep.stats && ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
+                    }
                     if (!ok) continue;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
-                    const int c0 = cb * 16;
                     if (ep.mode == OUT_PADDED_BF16) {
                         const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
                         if (ngroups <= 0) continue;
-                        const uint4 q0 = pack_bf16x8(v), q1 = pack_bf16x8(v + 8);
+                        const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
                         if (!edge_xy && z != 1 && z != Dd - 2) {
                             uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
                             *p = q0;
                             if (ngroups > 1) p[gstride] = q1;
                         } else {
-                            store_padded_groups(ep.dst, t.n, 2 * cb, ngroups, z, y, x, q0, q1);
+                            store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, y, x, q0, q1);
                         }
                     } else {
-                        float *o = fbase + (size_t)c0 * vol + (size_t)b * Hh * Ww;
+                        float *o = fbase + (size_t)(cb * 16) * vol + (size_t)b * Hh * Ww;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
                     }
+                }
+                if (ep.stats) {   // whole warp converged here: the b loop has a warp-uniform trip count
+                    __syncwarp();
+                    warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2);
                 }
             }
             tmem_wait_st();

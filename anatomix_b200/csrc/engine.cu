@@ -32,6 +32,27 @@ inline uint16_t f32_to_bf16_rne(float f) {
     u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+inline uint16_t f32_to_f16_rne(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0));   // inf / nan
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                                      // overflow -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                                   // underflow -> 0
+    if (x < 0x38800000u) {                                                                        // subnormal half
+        const int shift = 126 - (int)(x >> 23);              // 14..24
+        const uint32_t mant = (x & 0x7fffffu) | 0x800000u;
+        uint32_t h = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((x - 0x38000000u) >> 13);
+    const uint32_t rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+}
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -52,7 +73,7 @@ EncodeTiledFn load_encode_tiled() {
 }
 
 // ---------------------------------------------------------------- layer program
-enum StepKind { STEP_STEM, STEP_CONV, STEP_POOL, STEP_UP };
+enum StepKind { STEP_STEM, STEP_CONV, STEP_POOL, STEP_UP, STEP_NORM };
 
 struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     int module_index;         // position in the flat Sequential (state-dict key)
@@ -63,6 +84,9 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     // device parameters
     bool ready = false;
     int fold = 0, groups = 3;
+    int n_splits = 1, ncols_split = 0;        // Cout > 256: channel splits of 256 handled by different CTAs
+    bool inorm = false;                       // followed by InstanceNorm: raw output + statistics
+    size_t stats_index = 0;                   // first double of this conv's [N][ncols][2] block, per sample-channel
     void *d_wpack = nullptr;  // bf16 slabs (tensor-core convs) or fp32 [cin][27][cout] (stem)
     float *d_bias = nullptr;  // [ncols]
     size_t wpack_bytes = 0;
@@ -84,6 +108,8 @@ struct ShapePlan {            // everything that depends on (N, D, H, W, workspa
     int N = 0, D = 0, H = 0, W = 0;
     void *workspace = nullptr;
     std::vector<size_t> buf_offset;
+    size_t stats_offset = 0, stats_bytes = 0;   // instance-norm sums at the end of the workspace
+    std::vector<size_t> conv_stats_offset;      // per conv, bytes from workspace start
     std::vector<CUtensorMap> tmaps;   // per conv (unused for the stem)
     std::vector<ConvGeom> geoms;      // per conv
 };
@@ -92,6 +118,7 @@ struct ShapePlan {            // everything that depends on (N, D, H, W, workspa
 
 struct anx_engine {
     anx_unet_desc desc;
+    int dt = DT_BF16;         // storage type of activations / packed weights
     int num_sms = 148;
     int max_smem = 0;
     std::vector<ConvLayer> convs;
@@ -143,6 +170,9 @@ void add_conv(anx_engine *e, int &module_index, int cin, int cout, int level, bo
     c.src_buf = src;
     c.dst_buf = dst;
     c.dst_group_offset = dst_goff;
+    c.inorm = c.has_norm && d.norm_kind == ANX_NORM_INSTANCE;
+    c.n_splits = c.ncols > 256 ? c.ncols / 256 : 1;
+    c.ncols_split = c.ncols / c.n_splits;
     module_index += 1 + (c.has_norm ? 1 : 0) + (c.has_act ? 1 : 0);
     Step s{};
     s.kind = stem ? STEP_STEM : STEP_CONV;
@@ -150,6 +180,16 @@ void add_conv(anx_engine *e, int &module_index, int cin, int cout, int level, bo
     snprintf(s.name, sizeof s.name, "conv%d_%dto%d_L%d", c.module_index, cin, cout, level);
     e->convs.push_back(c);
     e->steps.push_back(s);
+    if (c.inorm) {   // normalise + activate in place once the whole tensor's statistics exist
+        Step nrm{};
+        nrm.kind = STEP_NORM;
+        nrm.conv = s.conv;
+        nrm.dst_buf = dst;
+        nrm.dst_group_offset = dst_goff;
+        nrm.groups = cout / 8;
+        snprintf(nrm.name, sizeof nrm.name, "inorm%d_L%d", c.module_index + 1, level);
+        e->steps.push_back(nrm);
+    }
 }
 
 // Walks the constructor logic of reference network.py:309-465 and lays out the
@@ -223,18 +263,20 @@ size_t buffer_bytes(const anx_engine *e, const Buffer &b, int n, int d, int h, i
 ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H, int W, int in_groups_total) {
     ConvGeom g{};
     g.N = N; g.D = D; g.H = H; g.W = W;
-    g.ncols = c.ncols;
+    g.ncols = c.ncols_split;
+    g.n_splits = c.n_splits;
+    g.dt = e->dt;
     g.fold = c.fold;
     g.groups = c.groups;
     g.cin_chunks = c.cin / 16;
     g.in_groups_total = in_groups_total;
     g.in_group_offset = 0;
     // output planes per tile: as many as TMEM double buffering allows, at most 8
-    int bz = std::max(1, std::min(8, 256 / c.ncols));
+    int bz = std::max(1, std::min(8, 256 / g.ncols));
     g.acc_stages = 2;
     bz = std::min(bz, D);
     g.bz = bz;
-    int cols = g.acc_stages * bz * c.ncols;
+    int cols = g.acc_stages * bz * g.ncols;
     int p2 = 32;
     while (p2 < cols) p2 *= 2;
     g.tmem_cols = p2;
@@ -242,10 +284,10 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.tiles_y = (H + TILE_Y - 1) / TILE_Y;
     g.tiles_z = (D + bz - 1) / bz;
     g.tiles_per_sample = g.tiles_x * g.tiles_y * g.tiles_z;
-    g.total_tiles = g.tiles_per_sample * N;
+    g.total_tiles = g.tiles_per_sample * N * g.n_splits;
     g.a_lbo = (uint32_t)(bz + 2) * HALO_Y * ROW_BYTES;
     g.a_stage_bytes = 2 * g.a_lbo;
-    g.b_rows = c.fold ? 3 * c.ncols : c.ncols;
+    g.b_rows = c.fold ? 3 * g.ncols : g.ncols;
     g.b_stage_bytes = 9 * 32 * g.b_rows;
     const size_t budget = (size_t)e->max_smem - sizeof(UmmaShared) - 1024;
     g.a_stages = 3;
@@ -289,6 +331,14 @@ anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, 
         p->buf_offset.push_back(off);
         off += buffer_bytes(e, b, N, D, H, W);
     }
+    p->stats_offset = off;
+    p->conv_stats_offset.assign(e->convs.size(), 0);
+    for (size_t i = 0; i < e->convs.size(); ++i)
+        if (e->convs[i].inorm) {
+            p->conv_stats_offset[i] = off;
+            off += align_up((size_t)N * e->convs[i].ncols * 2 * sizeof(double), 256);
+        }
+    p->stats_bytes = off - p->stats_offset;
     p->tmaps.resize(e->convs.size());
     p->geoms.resize(e->convs.size());
     for (size_t i = 0; i < e->convs.size(); ++i) {
@@ -325,9 +375,16 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
     Epilogue ep{};
     ep.cout = c.cout;
     ep.bias = c.d_bias;
-    ep.act = c.has_act ? e->desc.act_kind : ANX_ACT_NONE;
+    // with InstanceNorm the conv stores its raw output; the activation runs after the normalisation
+    ep.act = (c.has_act && !c.inorm) ? e->desc.act_kind : ANX_ACT_NONE;
     ep.slope = e->desc.act_slope;
+    ep.dt = e->dt;
     ep.stats = nullptr;
+    ep.stats_stride = c.ncols;
+    if (c.inorm) {
+        const size_t k = &c - e->convs.data();
+        ep.stats = reinterpret_cast<double *>(static_cast<char *>(p.workspace) + p.conv_stats_offset[k]);
+    }
     if (c.is_final) {
         ep.mode = OUT_NCDHW_F32;
         ep.out_f32 = out;
@@ -356,17 +413,17 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
     case STEP_STEM: {
         const ConvLayer &c = e->convs[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out);
-        const size_t vox = (size_t)p.N * p.D * p.H * p.W;
-        const int grid = grid_for(vox, 256, e->num_sms, 16);
         const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
+        const float *wp = (const float *)c.d_wpack;
+        auto grid_of = [&](int zt) { return dim3((p.W + 31) / 32, (p.H + 7) / 8, p.N * ((p.D + zt - 1) / zt)); };
         if (c.ncols == 16)
-            stem_conv_kernel<16><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<16, 4><<<grid_of(4), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
         else if (c.ncols == 32)
-            stem_conv_kernel<32><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<32, 2><<<grid_of(2), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
         else if (c.ncols == 48)
-            stem_conv_kernel<48><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<48, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
         else
-            stem_conv_kernel<64><<<grid, 256, sm, st>>>(in, (const float *)c.d_wpack, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<64, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
         break;
     }
     case STEP_CONV: {
@@ -375,7 +432,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         Epilogue ep = make_epilogue(e, p, c, out);
         if (force_simt) {
             ActView src = view_of(e, p, c.src_buf, 0);
-            const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols / 16);
+            const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
             conv3_simt_kernel<<<grid_for(items, 128, e->num_sms, 64), 128, 0, st>>>(
                 src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
         } else {
@@ -389,14 +446,29 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, 0);
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
         pool2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
-                                                                           e->desc.pool_kind);
+                                                                           e->desc.pool_kind, e->dt);
         break;
     }
     case STEP_UP: {
         ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, s.dst_group_offset);
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
-        upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
-                                                                               e->desc.interp_kind);
+        if (e->desc.interp_kind == ANX_INTERP_NEAREST)
+            upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
+        else
+            upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
+                                                                                   e->desc.interp_kind, e->dt);
+        break;
+    }
+    case STEP_NORM: {
+        const ConvLayer &c = e->convs[s.conv];
+        ActView t = view_of(e, p, s.dst_buf, s.dst_group_offset);
+        const size_t count = (size_t)(t.D + 2) * (t.H + 2) * (t.W + 2);
+        const double inv = 1.0 / ((double)t.D * t.H * t.W);
+        const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>(1024, (count + 2047) / 2048));
+        const double *stats = reinterpret_cast<const double *>(static_cast<char *>(p.workspace) + p.conv_stats_offset[s.conv]);
+        inorm_act_kernel<<<dim3(gx, (unsigned)(p.N * s.groups)), 256, 0, st>>>(
+            t, s.groups, stats, c.ncols, inv, e->desc.norm_eps, c.has_act ? e->desc.act_kind : ANX_ACT_NONE,
+            e->desc.act_slope, e->dt);
         break;
     }
     }
@@ -448,13 +520,18 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (!desc || !out || desc->struct_size != sizeof(anx_unet_desc)) return ANX_ERR_BAD_ARG;
     *out = nullptr;
     if (desc->input_nc < 1 || desc->output_nc < 1 || desc->output_nc > 256 || desc->num_downs < 1 ||
-        desc->num_downs > 7 || desc->ngf < 16 || desc->ngf % 16 != 0 || (desc->ngf << desc->num_downs) > 256)
+        desc->num_downs > 7 || desc->ngf < 16 || desc->ngf % 16 != 0 || (desc->ngf << desc->num_downs) > 1024)
         return ANX_ERR_UNSUPPORTED;
-    if (desc->norm_kind != ANX_NORM_NONE && desc->norm_kind != ANX_NORM_BATCH_EVAL) return ANX_ERR_UNSUPPORTED;
+    for (int i = 0; i <= desc->num_downs; ++i) {   // widths above 256 are split into 256-channel CTA slices
+        const int wdt = desc->ngf << i;
+        if (wdt > 256 && wdt % 256 != 0) return ANX_ERR_UNSUPPORTED;
+    }
+    if (desc->norm_kind < ANX_NORM_NONE || desc->norm_kind > ANX_NORM_INSTANCE) return ANX_ERR_BAD_ARG;
     if (desc->act_kind < ANX_ACT_NONE || desc->act_kind > ANX_ACT_LEAKY) return ANX_ERR_BAD_ARG;
     if (desc->pool_kind != ANX_POOL_MAX && desc->pool_kind != ANX_POOL_AVG) return ANX_ERR_BAD_ARG;
     if (desc->interp_kind != ANX_INTERP_NEAREST && desc->interp_kind != ANX_INTERP_TRILINEAR) return ANX_ERR_BAD_ARG;
     if (desc->ngf > 64 || desc->input_nc > 4) return ANX_ERR_UNSUPPORTED;
+    if ((desc->flags & ANX_FLAG_STORE_FP16) && (desc->flags & ANX_FLAG_STORE_BF16)) return ANX_ERR_BAD_ARG;
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || desc->device < 0 || desc->device >= ndev) return ANX_ERR_NO_DEVICE;
@@ -465,16 +542,21 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
 
     anx_engine *e = new anx_engine();
     e->desc = *desc;
+    // InstanceNorm bounds every stored activation, so fp16 (3 more mantissa bits than bf16) is safe and
+    // is needed to stay within tolerance through 24 normalised layers; BatchNorm networks keep bf16 range.
+    e->dt = desc->norm_kind == ANX_NORM_INSTANCE ? DT_FP16 : DT_BF16;
+    if (desc->flags & ANX_FLAG_STORE_FP16) e->dt = DT_FP16;
+    if (desc->flags & ANX_FLAG_STORE_BF16) e->dt = DT_BF16;
     e->num_sms = prop.multiProcessorCount;
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
     build_program(e);
     for (auto &c : e->convs) {
-        c.fold = (!c.is_stem && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
+        c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
     }
     cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (err != cudaSuccess) {
         delete e;
         return ANX_ERR_CUDA;
@@ -536,7 +618,7 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
             scale[o] = g1[o] / std::sqrt(g4[o] + e->desc.norm_eps);
             shift[o] = g2[o] - g3[o] * scale[o] + (bias ? hb[o] * scale[o] : 0.0f);
         }
-    } else if (bias) {
+    } else if (bias && !c.inorm) {   // a bias in front of InstanceNorm is cancelled by the mean subtraction
         for (int o = 0; o < c.cout; ++o) shift[o] = hb[o];
     }
 
@@ -554,21 +636,23 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
         ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
         ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
     } else {
-        // bf16 slabs [chunk][group][tap(ky,kx)][kchunk][row][8]; folded rows = (dz=+1 | 0 | -1) x ncols
-        const int R = c.fold ? 3 * c.ncols : c.ncols;
+        // 16-bit slabs [split][chunk][group][tap(ky,kx)][kchunk][row][8]; folded rows = (dz=+1 | 0 | -1) x ncols
+        const int W = c.ncols_split;
+        const int R = c.fold ? 3 * W : W;
         const int chunks = c.cin / 16;
         const size_t slab = (size_t)9 * 2 * R * 8;
-        std::vector<uint16_t> pk((size_t)chunks * c.groups * slab, 0);
+        std::vector<uint16_t> pk((size_t)c.n_splits * chunks * c.groups * slab, 0);
         for (int o = 0; o < c.cout; ++o)
             for (int i = 0; i < c.cin; ++i) {
                 const int ch = i / 16, kc = (i % 16) / 8, el = i % 8;
+                const int split = o / W, ol = o % W;
                 for (int kz = 0; kz < 3; ++kz) {
                     const int grp = c.fold ? 0 : kz;
-                    const int row = c.fold ? (2 - kz) * c.ncols + o : o;
+                    const int row = c.fold ? (2 - kz) * W + ol : ol;
                     for (int t = 0; t < 9; ++t) {
                         const float v = hw[((size_t)o * c.cin + i) * 27 + kz * 9 + t] * scale[o];
-                        pk[(size_t)(ch * c.groups + grp) * slab + ((size_t)(t * 2 + kc) * R + row) * 8 + el] =
-                            f32_to_bf16_rne(v);
+                        pk[((size_t)(split * chunks + ch) * c.groups + grp) * slab + ((size_t)(t * 2 + kc) * R + row) * 8 + el] =
+                            e->dt == DT_BF16 ? f32_to_bf16_rne(v) : f32_to_f16_rne(v);
                     }
                 }
             }
@@ -586,6 +670,8 @@ size_t anx_engine_workspace_bytes(const anx_engine *e, int32_t n, int32_t d, int
     if (!e || !shape_ok(e, n, d, h, w)) return 0;
     size_t total = 0;
     for (auto &b : e->bufs) total += buffer_bytes(e, b, n, d, h, w);
+    for (auto &c : e->convs)
+        if (c.inorm) total += align_up((size_t)n * c.ncols * 2 * sizeof(double), 256);
     return total;
 }
 
@@ -616,6 +702,9 @@ anx_status anx_engine_forward(anx_engine *e, const float *in, float *out, int32_
     std::shared_ptr<ShapePlan> p;
     st = get_plan(e, n, d, h, w, workspace, p);
     if (st != ANX_OK) return st;
+    if (p->stats_bytes)
+        ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes,
+                                    static_cast<cudaStream_t>(stream)));
     for (auto &s : e->steps) {
         st = launch_step(e, *p, s, in, out, static_cast<cudaStream_t>(stream));
         if (st != ANX_OK) return st;
@@ -652,6 +741,8 @@ anx_status anx_engine_profile(anx_engine *e, const float *in, float *out, int32_
     const int k = (int)e->steps.size();
     std::vector<cudaEvent_t> ev(k + 1);
     for (auto &x : ev) ANX_CUDA(e, cudaEventCreate(&x));
+    if (p->stats_bytes)
+        ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes, s));
     ANX_CUDA(e, cudaEventRecord(ev[0], s));
     for (int i = 0; i < k; ++i) {
         st = launch_step(e, *p, e->steps[i], in, out, s);

@@ -2,6 +2,8 @@
 // either into the next layer's reflect-padded planar bf16 buffer (writing the
 // mirrored shell copies as well) or into the fp32 NCDHW network output.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "layout.cuh"
 
 namespace anx {
@@ -10,18 +12,58 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
-__device__ __forceinline__ uint4 pack_bf16x8(const float *v) {
-    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                      pack_bf16x2(v[6], v[7]));
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
 }
-__device__ __forceinline__ void unpack_bf16x8(const uint4 &q, float *v) {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
+// 8 floats -> 16 bytes of the storage type (round to nearest even)
+__device__ __forceinline__ uint4 pack_x8(const float *v, int dt) {
+    if (dt == DT_BF16)
+        return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                          pack_bf16x2(v[6], v[7]));
+    return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                      pack_f16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack_x8(const uint4 &q, float *v, int dt) {
+    if (dt == DT_BF16) {
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 f = __bfloat1622float2(h[i]);
-        v[2 * i] = f.x;
-        v[2 * i + 1] = f.y;
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    } else {
+        const __half2 *h = reinterpret_cast<const __half2 *>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __half22float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
     }
+}
+
+// Warp-level instance-norm statistics: every lane brings 16 per-channel partial sums
+// `s` and 16 partial sums of squares `q` (its own voxels).  A butterfly
+// reduce-scatter (31 shuffles for the 32 values) leaves lane l with the warp total of
+// value l, which it adds to `stats16[(l & 15) * 2 + (l >> 4)]` in double precision.
+__device__ __forceinline__ void warp_stats_add(const float *s, const float *q, double *stats16) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = s[i]; v[16 + i] = q[i]; }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+            const float keep = up ? v[i + m] : v[i];
+            const float send = up ? v[i] : v[i + m];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    atomicAdd(stats16 + (lane & 15) * 2 + (lane >> 4), (double)v[0]);
 }
 
 // Padded-coordinate targets of interior coordinate v on an axis of size S:
@@ -66,15 +108,25 @@ __device__ __forceinline__ float activate(float v, int act, float slope) {
     return v;
 }
 
-// v[16]: raw accumulators of channels [16*cb, 16*cb+16) of voxel (n,z,y,x).
+// v[16]: raw accumulators of channels [16*cb, 16*cb+16) of voxel (n,z,y,x).  Used by
+// the CUDA-core kernels (stem, debug conv); statistics go out one atomic per value
+// there, the tensor-core kernel has its own warp-reduced path.
 __device__ __forceinline__ void epilogue_store16(const Epilogue &ep, int n, int z, int y, int x, int cb, float *v) {
     const int c0 = cb * 16;
+    if (ep.stats) {
+        double *st = ep.stats + ((size_t)n * ep.stats_stride + c0) * 2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            atomicAdd(st + 2 * i, (double)v[i]);
+            atomicAdd(st + 2 * i + 1, (double)v[i] * (double)v[i]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + __ldg(ep.bias + c0 + i), ep.act, ep.slope);
     if (ep.mode == OUT_PADDED_BF16) {
         const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
         if (ngroups <= 0) return;
-        store_padded_groups(ep.dst, n, 2 * cb, ngroups, z, y, x, pack_bf16x8(v), pack_bf16x8(v + 8));
+        store_padded_groups(ep.dst, n, 2 * cb, ngroups, z, y, x, pack_x8(v, ep.dt), pack_x8(v + 8, ep.dt));
     } else {
         const size_t plane = (size_t)ep.dst.D * ep.dst.H * ep.dst.W;
         float *o = ep.out_f32 + ((size_t)n * ep.cout + c0) * plane + ((size_t)z * ep.dst.H + y) * ep.dst.W + x;

@@ -41,15 +41,19 @@ enum OutMode : int {
     OUT_NCDHW_F32 = 1       // network output, fp32 [N, C, D, H, W]
 };
 
+enum StoreType : int { DT_BF16 = 0, DT_FP16 = 1 };   // 16-bit storage type of activations / packed weights
+
 struct Epilogue {
     int mode;
-    ActView dst;            // OUT_PADDED_BF16
+    ActView dst;            // OUT_PADDED_BF16 (name kept; holds bf16 or fp16 per `dt`)
     float *out_f32;         // OUT_NCDHW_F32
-    int cout;               // real output channels (<= padded ncols)
-    const float *bias;      // [ncols] folded BN shift / conv bias (zeros if none)
+    int cout;               // real output channels of the whole conv
+    const float *bias;      // [cout rounded up to 16] folded BN shift / conv bias (zeros if none)
     int act;                // 0 none, 1 relu, 2 leaky
     float slope;
-    float *stats;           // instance-norm partial sums [N][ncols][2] (sum, sumsq) or nullptr
+    int dt;                 // StoreType of dst
+    double *stats;          // instance-norm sums [N][cout_padded][2] (sum, sum of squares) or nullptr
+    int stats_stride;       // cout rounded up to 16 (channels per sample in `stats`)
 };
 
 // tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),
@@ -67,7 +71,9 @@ struct ConvGeom {
     int cin_chunks;         // Cin / 16
     int in_groups_total;    // groups per sample in the INPUT buffer (TMA dim 3 = n * this + g)
     int in_group_offset;
-    int ncols;              // Cout rounded up to 16 (TMEM columns per output plane)
+    int ncols;              // output channels handled per CTA tile, multiple of 16 (TMEM columns per plane)
+    int n_splits;           // Cout > 256 is split over CTAs: tile -> (spatial tile, split); channel0 = split*ncols
+    int dt;                 // StoreType of the input activations and packed weights
     int fold;               // 1: one MMA covers the three dz taps (N = 3*ncols)
     int groups;             // B stages per chunk: 1 when folded, 3 (one per dz) otherwise
     int acc_stages;         // TMEM accumulator double buffering

@@ -62,6 +62,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
     }
 }
 
+// Warp-collective wait: every lane polls, the loop condition is a vote, so the
+// compiler keeps the surrounding code warp-uniform (uniform registers for the MMA
+// descriptors that follow).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int tag = 0) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (clock64() - t0 > 6000000000LL) {
+            if ((threadIdx.x & 31) == 0)
+                printf("anx: mbarrier watchdog block %d warp %d tag %d parity %u\n", blockIdx.x, threadIdx.x >> 5, tag,
+                       parity);
+            __trap();
+        }
+    }
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -150,6 +166,11 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswz(uint32_t saddr, uint3
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 D, M=128.
 __host__ __device__ __forceinline__ uint32_t idesc_bf16_m128(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// Same with the A/B element type selectable: dt 0 = bf16 (format 1), 1 = fp16 (format 0).
+__host__ __device__ __forceinline__ uint32_t idesc_m128(uint32_t n, int dt) {
+    const uint32_t fmt = dt == 0 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // 32 lanes x 16 columns of fp32 -> 16 registers per thread (lane = row).

@@ -10,49 +10,89 @@ namespace anx {
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 // ------------------------------------------------------------------ stem conv
-// in: fp32 [N, CIN, D, H, W]; w: fp32 [CIN][27][COUT] (BN folded); one thread
-// per voxel computes all COUT channels.  Memory-bound (reads 4 B, writes
-// 2*COUT B per voxel), so CUDA cores are the right tool (K = 27 is far too thin
-// for a tensor-core tile).
-template <int COUT>
-__global__ void __launch_bounds__(256)
+// in: fp32 [N, CIN, D, H, W]; w: fp32 [CIN][27][COUT] (BN folded).  K = 27*CIN is far
+// too thin for a tensor-core tile, so this runs on the CUDA cores: a thread owns ZT
+// consecutive z voxels at one (y, x) and all COUT channels (COUT*ZT accumulators);
+// lanes run along x so every load and store is coalesced, and each loaded input
+// value feeds up to 3 output planes.  FFMA-bound (432 FMA per voxel for 1->16).
+template <int COUT, int ZT>
+__global__ void __launch_bounds__(256, 2)
 stem_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, int cin, int N, int D, int H, int W,
                  Epilogue ep) {
     extern __shared__ float sw[];   // [cin][27][COUT]
     for (int i = threadIdx.x; i < cin * 27 * COUT; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int ztiles = (D + ZT - 1) / ZT;
+    const int n = blockIdx.z / ztiles;
+    const int z0 = (blockIdx.z - n * ztiles) * ZT;
+    const bool valid = (x < W) && (y < H);       // no early exit: the statistics path shuffles across the warp
     const size_t plane = (size_t)D * H * W;
-    const size_t total = (size_t)N * plane;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
-        const int n = (int)(v / plane);
-        size_t r = v - (size_t)n * plane;
-        const int z = (int)(r / ((size_t)H * W));
-        r -= (size_t)z * H * W;
-        const int y = (int)(r / W), x = (int)(r - (size_t)y * W);
-        float acc[COUT];
+    float acc[ZT][COUT];
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) acc[i] = 0.0f;
-        for (int ci = 0; ci < cin; ++ci) {
-            const float *src = in + ((size_t)n * cin + ci) * plane;
+    for (int o = 0; o < ZT; ++o)
 #pragma unroll
-            for (int kz = 0; kz < 3; ++kz) {
-                const int zz = reflect_idx(z + kz - 1, D);
+        for (int i = 0; i < COUT; ++i) acc[o][i] = 0.0f;
+    int xx[3], yy[3];
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int yy = reflect_idx(y + ky - 1, H);
-                    const float *row = src + ((size_t)zz * H + yy) * W;
+    for (int k = 0; k < 3; ++k) {
+        xx[k] = reflect_idx(valid ? x + k - 1 : 0, W);
+        yy[k] = reflect_idx(valid ? y + k - 1 : 0, H);
+    }
+    for (int ci = 0; ci < cin; ++ci) {
+        const float *src = in + ((size_t)n * cin + ci) * plane;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float a = __ldg(row + reflect_idx(x + kx - 1, W));
-                        const float *wt = sw + (ci * 27 + (kz * 3 + ky) * 3 + kx) * COUT;
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int i = 0; i < COUT; ++i) acc[i] = fmaf(a, wt[i], acc[i]);
+            for (int kx = 0; kx < 3; ++kx) {
+                const float *col = src + (size_t)yy[ky] * W + xx[kx];
+                float a[ZT + 2];
+#pragma unroll
+                for (int pz = 0; pz < ZT + 2; ++pz) {
+                    int zz = z0 + pz - 1;                          // beyond D only for masked outputs
+                    zz = reflect_idx(zz < D ? zz : D, D);
+                    a[pz] = __ldg(col + (size_t)zz * H * W);
+                }
+#pragma unroll
+                for (int kz = 0; kz < 3; ++kz) {
+                    const float *wt = sw + (ci * 27 + (kz * 3 + ky) * 3 + kx) * COUT;
+#pragma unroll
+                    for (int i = 0; i < COUT; ++i) {
+                        const float wv = wt[i];
+#pragma unroll
+                        for (int o = 0; o < ZT; ++o) acc[o][i] = fmaf(a[o + kz], wv, acc[o][i]);
                     }
                 }
             }
-        }
+    }
+    if (ep.stats) {   // instance norm: warp-reduced sums of the raw conv output (lanes = 32 x voxels of sample n)
 #pragma unroll
-        for (int cb = 0; cb < COUT / 16; ++cb) epilogue_store16(ep, n, z, y, x, cb, acc + cb * 16);
+        for (int cb = 0; cb < COUT / 16; ++cb) {
+            float s16[16], q16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
+#pragma unroll
+            for (int o = 0; o < ZT; ++o)
+                if (valid && z0 + o < D) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float v = acc[o][cb * 16 + i];
+                        s16[i] += v;
+                        q16[i] = fmaf(v, v, q16[i]);
+                    }
+                }
+            warp_stats_add(s16, q16, ep.stats + ((size_t)n * ep.stats_stride + cb * 16) * 2);
+        }
+    }
+    Epilogue ep_store = ep;
+    ep_store.stats = nullptr;
+    if (!valid) return;
+#pragma unroll
+    for (int o = 0; o < ZT; ++o) {
+        if (z0 + o >= D) break;
+#pragma unroll
+        for (int cb = 0; cb < COUT / 16; ++cb) epilogue_store16(ep_store, n, z0 + o, y, x, cb, acc[o] + cb * 16);
     }
 }
 
@@ -62,7 +102,7 @@ stem_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, int 
 __global__ void __launch_bounds__(128)
 conv3_simt_kernel(ActView src, ConvGeom g, const __nv_bfloat16 *__restrict__ wpack, Epilogue ep) {
     const size_t plane = (size_t)g.D * g.H * g.W;
-    const int cblocks = g.ncols / 16;
+    const int cblocks = g.ncols * g.n_splits / 16;   // all output channels, every split
     const size_t total = (size_t)g.N * plane * cblocks;
     const size_t slab = (size_t)9 * 2 * g.b_rows * 8;   // elements per (chunk, group)
     for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
@@ -79,16 +119,17 @@ conv3_simt_kernel(ActView src, ConvGeom g, const __nv_bfloat16 *__restrict__ wpa
             for (int kz = 0; kz < 3; ++kz) {
                 const int grp = g.fold ? 0 : kz;
                 const int rowbase = g.fold ? (2 - kz) * g.ncols : 0;   // blocks ordered dz = +1, 0, -1
-                const __nv_bfloat16 *wb = wpack + (size_t)(c * g.groups + grp) * slab;
+                const int split = cb * 16 / g.ncols, cl = cb * 16 - split * g.ncols;   // channel slice and offset in it
+                const __nv_bfloat16 *wb = wpack + ((size_t)(split * g.cin_chunks + c) * g.groups + grp) * slab;
                 for (int t = 0; t < 9; ++t) {
                     const int ky = t / 3, kx = t % 3;
                     for (int kc = 0; kc < 2; ++kc) {
                         float a[8];
-                        unpack_bf16x8(*src.at(n, 2 * c + kc, z + kz, y + ky, x + kx), a);
-                        const __nv_bfloat16 *wr = wb + ((size_t)(t * 2 + kc) * g.b_rows + rowbase + cb * 16) * 8;
+                        unpack_x8(*src.at(n, 2 * c + kc, z + kz, y + ky, x + kx), a, g.dt);
+                        const __nv_bfloat16 *wr = wb + ((size_t)(t * 2 + kc) * g.b_rows + rowbase + cl) * 8;
                         for (int i = 0; i < 16; ++i) {
                             float wv[8];
-                            unpack_bf16x8(*reinterpret_cast<const uint4 *>(wr + i * 8), wv);
+                            unpack_x8(*reinterpret_cast<const uint4 *>(wr + i * 8), wv, g.dt);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) acc[i] = fmaf(a[e], wv[e], acc[i]);
                         }
@@ -103,7 +144,7 @@ conv3_simt_kernel(ActView src, ConvGeom g, const __nv_bfloat16 *__restrict__ wpa
 // 2x2x2 stride-2 max / mean (reference network.py:297,368); one thread per output
 // voxel and 8-channel group; writes the pooled tensor with its reflect shell.
 __global__ void __launch_bounds__(256)
-pool2_kernel(ActView src, ActView dst, int N, int groups, int kind) {
+pool2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt) {
     const size_t total = (size_t)N * groups * dst.D * dst.H * dst.W;
     for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
         size_t v = id;
@@ -122,7 +163,7 @@ pool2_kernel(ActView src, ActView dst, int N, int groups, int kind) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float f[8];
-                    unpack_bf16x8(*src.at(n, gidx, 2 * z + a + 1, 2 * y + b + 1, 2 * x + c + 1), f);
+                    unpack_x8(*src.at(n, gidx, 2 * z + a + 1, 2 * y + b + 1, 2 * x + c + 1), f, dt);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) m[i] = kind == 0 ? fmaxf(m[i], f[i]) : m[i] + f[i];
                 }
@@ -130,7 +171,7 @@ pool2_kernel(ActView src, ActView dst, int N, int groups, int kind) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) m[i] *= 0.125f;
         }
-        const uint4 q = pack_bf16x8(m);
+        const uint4 q = pack_x8(m, dt);
         store_padded_groups(dst, n, gidx, 1, z, y, x, q, q);
     }
 }
@@ -145,8 +186,28 @@ __device__ __forceinline__ void tri_src(int o, int n, int &i0, int &i1, float &t
     t = s - (float)i0;
 }
 
+// nearest only: one thread per (low z, low y, HIGH x); it reads its low-res voxel
+// once and writes the 2x2 (z, y) copies, so every store is a coalesced 512-byte run.
 __global__ void __launch_bounds__(256)
-upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind) {
+upsample2_nearest_kernel(ActView src, ActView dst, int N, int groups) {
+    const size_t total = (size_t)N * groups * src.D * src.H * dst.W;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+        size_t v = id;
+        const int x = (int)(v % dst.W); v /= dst.W;
+        const int yl = (int)(v % src.H); v /= src.H;
+        const int zl = (int)(v % src.D); v /= src.D;
+        const int gidx = (int)(v % groups);
+        const int n = (int)(v / groups);
+        const uint4 q = *src.at(n, gidx, zl + 1, yl + 1, (x >> 1) + 1);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) store_padded_groups(dst, n, gidx, 1, 2 * zl + a, 2 * yl + b, x, q, q);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt) {
     const size_t total = (size_t)N * groups * dst.D * dst.H * dst.W;
     for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
         size_t v = id;
@@ -175,13 +236,48 @@ upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind) {
                     for (int c = 0; c < 2; ++c) {
                         const float wgt = (a ? tz : 1.0f - tz) * (b ? ty : 1.0f - ty) * (c ? tx : 1.0f - tx);
                         float f[8];
-                        unpack_bf16x8(*src.at(n, gidx, (a ? z1 : z0) + 1, (b ? y1 : y0) + 1, (c ? x1 : x0) + 1), f);
+                        unpack_x8(*src.at(n, gidx, (a ? z1 : z0) + 1, (b ? y1 : y0) + 1, (c ? x1 : x0) + 1), f, dt);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] = fmaf(wgt, f[i], o[i]);
                     }
-            q = pack_bf16x8(o);
+            q = pack_x8(o, dt);
         }
         store_padded_groups(dst, n, gidx, 1, z, y, x, q, q);
+    }
+}
+
+// ---------------------------------------------------------- instance norm + act
+// In place over one tensor inside a padded planar buffer, shell included (the shell
+// holds mirror copies, so normalising it element-wise equals mirroring afterwards):
+//   y = act((x - mean[n,c]) * rsqrt(var[n,c] + eps)),  biased variance
+// (nn.InstanceNorm3d(affine=False), reference network.py:157-158).  mean / var come
+// from the double-precision sums the producing conv accumulated from its fp32
+// accumulators.  blockIdx.y = n * groups + g; blockIdx.x strides over the plane.
+__global__ void __launch_bounds__(256)
+inorm_act_kernel(ActView t, int groups, const double *__restrict__ stats, int stats_stride, double inv_count,
+                 float eps, int act, float slope, int dt) {
+    __shared__ float s_mean[8], s_rstd[8];
+    const int n = blockIdx.y / groups, gidx = blockIdx.y - n * groups;
+    if (threadIdx.x < 8) {
+        const double *st = stats + ((size_t)n * stats_stride + gidx * 8 + threadIdx.x) * 2;
+        const double m = st[0] * inv_count;
+        double var = st[1] * inv_count - m * m;
+        var = var > 0.0 ? var : 0.0;
+        s_mean[threadIdx.x] = (float)m;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mean[i] = s_mean[i]; rstd[i] = s_rstd[i]; }
+    const size_t count = (size_t)(t.D + 2) * (t.H + 2) * (t.W + 2);
+    uint4 *base = t.at(n, gidx, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack_x8(base[i], v, dt);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = activate((v[k] - mean[k]) * rstd[k], act, slope);
+        base[i] = pack_x8(v, dt);
     }
 }
 

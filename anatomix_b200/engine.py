@@ -210,13 +210,14 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
     if cfg["norm"] == "batch":
         if module.training:
             return "BatchNorm in train mode uses batch statistics"
-    elif cfg["norm"] != "none":
-        return f"norm {cfg['norm']!r} not on the engine yet"
+    elif cfg["norm"] not in ("none", "instance"):
+        return f"norm {cfg['norm']!r} is not handled by the engine"
     if cfg["activation"] not in ("relu", "lrelu", "none"):
         return "activation not supported"
     if cfg["pooling"] not in ("Max", "Avg") or cfg["interp"] not in ("nearest", "trilinear"):
         return "pooling / interpolation not supported"
-    if cfg["ngf"] % 16 != 0 or cfg["ngf"] > 64 or (cfg["ngf"] << cfg["num_downs"]) > 256 \
+    widths = [cfg["ngf"] << i for i in range(cfg["num_downs"] + 1)]
+    if cfg["ngf"] % 16 != 0 or cfg["ngf"] > 64 or widths[-1] > 1024 or any(w > 256 and w % 256 for w in widths) \
             or cfg["input_nc"] > 4 or cfg["output_nc"] > 256:
         return "channel widths outside the tensor-core kernel's range"
     if x.shape[1] != cfg["input_nc"]:

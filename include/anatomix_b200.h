@@ -68,6 +68,12 @@ typedef struct anx_unet_desc {
 
 /* debugging / measurement switches */
 #define ANX_FLAG_FORCE_SIMT 1u   /* run every conv on the CUDA-core debug kernel  */
+/* 16-bit storage type of activations and packed weights (fp32 accumulate either way).
+ * Default: bf16 for BatchNorm / no-norm networks (activations are unbounded), fp16 for
+ * InstanceNorm networks (every stored tensor is bounded by the normalisation and the
+ * extra mantissa bits are needed through 24 normalised layers). */
+#define ANX_FLAG_STORE_FP16 2u
+#define ANX_FLAG_STORE_BF16 4u
 
 /* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
  * device constants; no parameters yet. */

@@ -18,9 +18,10 @@ the plain-C restatement ``unet_ref.c``) against them.
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this module.
 
-``engine_rounding=True`` reproduces where the B200 engine rounds to bf16
-(packed weights, stored activations) while accumulating in fp32, which gives the
-tight parity gate of SURVEY.md section 8(c).
+``engine_rounding=True`` reproduces where the B200 engine rounds to its storage
+type (packed weights, stored activations; bf16 for BatchNorm networks, fp16 for
+InstanceNorm networks whose activations are bounded by the normalisation) while
+accumulating in fp32, which gives the tight parity gate of SURVEY.md section 8(c).
 """
 from __future__ import annotations
 
@@ -82,6 +83,13 @@ def _bf16(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def engine_storage_dtype(cfg):
+    """Storage type the engine picks for a configuration."""
+    c = dict(DEFAULTS)
+    c.update(cfg)
+    return torch.float16 if c["norm"] == "instance" else torch.bfloat16
+
+
 def _activate(x, kind):
     if kind == "relu":
         return F.relu(x)                       # network.py:188-189
@@ -115,6 +123,8 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
         c["input_nc"], c["output_nc"], c["num_downs"], c["ngf"], c["norm"],
         c["activation"], c["final_act"], c["doubleconv"], c["use_skip_connection"])
     g = lambda k: torch.as_tensor(state[k]).to(torch.float32)
+    sdt = engine_storage_dtype(c)
+    _rnd = lambda t: t.to(sdt).to(torch.float32)
     feat, skips, taps = x.to(torch.float32), [], []
     eps = c["norm_eps"]
     n_conv = 0
@@ -130,7 +140,9 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
                     w = w * s.view(-1, 1, 1, 1, 1)
                     b = g(f"model.{idx+1}.bias") - g(f"model.{idx+1}.running_mean") * s
                 if n_conv > 0:                       # stem conv stays fp32
-                    w = _bf16(w)
+                    w = _rnd(w)
+                if nxt == "norm" and c["norm"] == "instance":
+                    b = None                         # cancelled by the normalisation; engine drops it
             feat = conv3d_reflect(feat, w, b)
             n_conv += 1
         elif op == "norm":
@@ -144,27 +156,33 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
                         g(f"model.{idx}.weight"), g(f"model.{idx}.bias"),
                         training=training, momentum=0.1, eps=eps)
             elif c["norm"] == "instance":            # network.py:157-158
-                feat = F.instance_norm(feat, eps=eps)
+                if engine_rounding:
+                    # statistics from the fp32 accumulators, applied to the stored (rounded) conv output
+                    mean = feat.mean(dim=(2, 3, 4), keepdim=True)
+                    var = feat.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+                    feat = (_rnd(feat) - mean) * torch.rsqrt(var + eps)
+                else:
+                    feat = F.instance_norm(feat, eps=eps)
             elif c["norm"] == "instance_affine":
                 feat = F.instance_norm(feat, weight=g(f"model.{idx}.weight"),
                                        bias=g(f"model.{idx}.bias"), eps=eps)
         elif op == "act":
             feat = _activate(feat, c["activation"])
             if engine_rounding:
-                feat = _bf16(feat)                   # activations live in HBM as bf16
+                feat = _rnd(feat)                    # activations live in HBM in the storage type
         elif op == "final_act":
             feat = _activate(feat, c["final_act"])
         elif op == "pool":                           # network.py:297,368
             feat = (F.max_pool3d if c["pooling"] == "Max" else F.avg_pool3d)(feat, 2)
             if engine_rounding:
-                feat = _bf16(feat)
+                feat = _rnd(feat)
         elif op == "up":                             # network.py:407
             if c["interp"] == "nearest":
                 feat = F.interpolate(feat, scale_factor=2, mode="nearest")
             else:
                 feat = F.interpolate(feat, scale_factor=2, mode=c["interp"])
                 if engine_rounding:
-                    feat = _bf16(feat)
+                    feat = _rnd(feat)
         if c["use_skip_connection"]:                 # network.py:543-547
             if idx in dec_idx:
                 feat = torch.cat((skips.pop(), feat), dim=1)

@@ -57,7 +57,7 @@ def compare(eng, cfg, state, x, emulate=True):
     for buf, idx, _ in prods:
         off, nb, lvl, grp = table[buf]
         want = to_padded_planar(tap[idx])
-        got = ws[off:off + want.numel() * 2].view(torch.bfloat16).float().cpu().view(want.shape)
+        got = ws[off:off + want.numel() * 2].view(O.engine_storage_dtype(cfg)).float().cpu().view(want.shape)
         inner = (slice(None), slice(None), slice(1, -1), slice(1, -1), slice(1, -1))
         den = want.norm().clamp_min(1e-20)
         rel_all = ((got - want).norm() / den).item()

@@ -58,10 +58,11 @@ def localize(eng_a, eng_b, shape):
     """Per-buffer comparison of two engines' workspaces after a forward."""
     n, _, d, h, w = shape
     wa, wb = eng_a.workspace(n, d, h, w), eng_b.workspace(n, d, h, w)
+    sdt = O.engine_storage_dtype(eng_a.cfg)
     lines = []
     for i, (off, nb, lvl, grp) in enumerate(eng_a.buffer_table(n, d, h, w)):
-        a = wa[off:off + nb].view(torch.bfloat16).float()
-        b = wb[off:off + nb].view(torch.bfloat16).float()
+        a = wa[off:off + nb].view(sdt).float()
+        b = wb[off:off + nb].view(sdt).float()
         finite = torch.isfinite(a) & torch.isfinite(b)
         diff = (a - b)[finite].abs().max().item() if finite.any() else float("nan")
         lines.append(f"buffer {i:2d} level {lvl} groups {grp:3d}: max|diff| {diff:.4g} "
@@ -123,6 +124,59 @@ def test_tensor_core_path_matches_simt_and_oracle_small(shape, cfgkw):
     report = compare(eng, full, state, x)
     first = [float(l.split("interior")[1].split()[0]) for l in report.splitlines()[:2]]
     assert max(first) < 1e-3, report
+
+
+@pytest.mark.parametrize("shape,cfgkw", [
+    ((1, 1, 16, 16, 8), dict(norm="instance", pooling="Avg", interp="trilinear", norm_eps=1e-2)),
+    ((2, 1, 8, 16, 24), dict(norm="instance", num_downs=1, ngf=32, output_nc=32, norm_eps=1e-2)),
+    ((1, 1, 16, 16, 16), dict(norm="instance", num_downs=3, ngf=64, output_nc=8, pooling="Avg",
+                              interp="trilinear", norm_eps=1e-2)),     # 512-wide bottleneck: channel splits
+])
+def test_instance_norm_path_small(shape, cfgkw):
+    """InstanceNorm networks: statistics from the fp32 accumulators, fp16 storage,
+    normalise + ReLU pass, AvgPool / trilinear, Cout > 256 split across CTAs."""
+    from anatomix_b200 import _lib
+    cfg = small_cfg(**cfgkw)
+    state = O.random_state(cfg, seed=21)
+    x = rand_input(shape, 13)
+    ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
+    eng = make_engine(cfg, state)
+    xs = x.cuda()
+    y_ref = ref_eng.forward(xs)
+    y = eng.forward(xs)
+    torch.cuda.synchronize()
+    r = rel_l2(y.cpu(), y_ref.cpu())
+    assert r < 5e-3, f"tensor-core vs CUDA-core conv: rel-L2 {r:.3e}\n" + localize(eng, ref_eng, shape)
+    check_against_oracle(cfg, state, x, y)
+    y2 = eng.forward(xs)                       # statistics buffers are re-zeroed every forward
+    torch.cuda.synchronize()
+    assert rel_l2(y2.cpu(), y.cpu()) < 1e-3
+
+
+def test_g4_dev_variant_94m_seeded_init():
+    """anatomix-dev (94M) config with the reference constructor's seeded default init
+    (its released weights are Hub-only): golden G4 from the unmodified reference."""
+    from conftest import CFG_94M
+    from anatomix_b200 import Unet
+    g = golden("g4_94m_64.npz")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_94M)
+    sd = m.state_dict()
+    x = rand_input((1, 1, 64, 64, 64), 0)
+    eng = make_engine(CFG_94M, sd)
+    y = eng.forward(x.cuda()).cpu()
+    want = torch.from_numpy(g["out_s2"])
+    got = y[:, :, ::2, ::2, ::2]
+    r, c = rel_l2(got, want), min_cosine(got, want)
+    assert r <= LOOSE_REL and c >= LOOSE_COS, f"G4: rel-L2 {r:.3e}, min cosine {c:.5f}"
+    emu = O.unet_forward(CFG_94M, sd, x, engine_rounding=True)
+    assert rel_l2(y, emu) <= TIGHT_REL, f"G4 tight: {rel_l2(y, emu):.3e}"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(x.cuda()) is None
+        ym = m(x.cuda()).cpu()
+    assert rel_l2(ym, y) < 1e-3
 
 
 def test_g1_smallest_legal_size(state_6m):
