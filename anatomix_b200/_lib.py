@@ -21,6 +21,7 @@ INTERP = {"nearest": 0, "trilinear": 1}
 FLAG_FORCE_SIMT = 1
 FLAG_STORE_FP16 = 2
 FLAG_STORE_BF16 = 4
+FLAG_DEPTH_HALO_INPUT = 8
 
 # every symbol include/anatomix_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -29,6 +30,7 @@ EXPORTS = [
     "anx_engine_forward_host", "anx_engine_launches_per_forward", "anx_engine_profile",
     "anx_engine_num_buffers", "anx_engine_buffer_info", "anx_status_string",
     "anx_engine_last_error", "anx_version", "anx_selftest",
+    "anx_engine_num_steps", "anx_engine_step_info", "anx_engine_run_steps",
 ]
 
 
@@ -87,6 +89,12 @@ def load():
     lib.anx_engine_buffer_info.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(sz), C.POINTER(sz),
                                            C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_buffer_info.restype = i32
+    lib.anx_engine_num_steps.argtypes = [vp]
+    lib.anx_engine_num_steps.restype = i32
+    lib.anx_engine_step_info.argtypes = [vp, i32] + [C.POINTER(i32)] * 4 + [C.c_char_p]
+    lib.anx_engine_step_info.restype = i32
+    lib.anx_engine_run_steps.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, sz, vp, i32, i32]
+    lib.anx_engine_run_steps.restype = i32
     lib.anx_status_string.argtypes = [i32]
     lib.anx_status_string.restype = C.c_char_p
     lib.anx_engine_last_error.argtypes = [vp]

@@ -417,13 +417,16 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const float *wp = (const float *)c.d_wpack;
         auto grid_of = [&](int zt) { return dim3((p.W + 31) / 32, (p.H + 7) / 8, p.N * ((p.D + zt - 1) / zt)); };
         if (c.ncols == 16)
-            stem_conv_kernel<16, 4><<<grid_of(4), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
+        const int zh = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
+        const int zh = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
+        if (c.ncols == 16)
+            stem_conv_kernel<16, 4><<<grid_of(4), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, zh, ep);
         else if (c.ncols == 32)
-            stem_conv_kernel<32, 2><<<grid_of(2), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<32, 2><<<grid_of(2), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, zh, ep);
         else if (c.ncols == 48)
-            stem_conv_kernel<48, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<48, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, zh, ep);
         else
-            stem_conv_kernel<64, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, ep);
+            stem_conv_kernel<64, 1><<<grid_of(1), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, zh, ep);
         break;
     }
     case STEP_CONV: {
@@ -707,6 +710,47 @@ anx_status anx_engine_forward(anx_engine *e, const float *in, float *out, int32_
                                     static_cast<cudaStream_t>(stream)));
     for (auto &s : e->steps) {
         st = launch_step(e, *p, s, in, out, static_cast<cudaStream_t>(stream));
+        if (st != ANX_OK) return st;
+    }
+    return ANX_OK;
+}
+
+int32_t anx_engine_num_steps(const anx_engine *e) { return e ? (int32_t)e->steps.size() : -1; }
+
+anx_status anx_engine_step_info(const anx_engine *e, int32_t step, int32_t *kind, int32_t *out_buffer,
+                                int32_t *out_group_offset, int32_t *out_groups, char name[32]) {
+    if (!e || step < 0 || step >= (int)e->steps.size()) return ANX_ERR_BAD_ARG;
+    const Step &s = e->steps[step];
+    int buf = s.dst_buf, goff = s.dst_group_offset, groups = s.groups;
+    if (s.kind == STEP_STEM || s.kind == STEP_CONV) {
+        const ConvLayer &c = e->convs[s.conv];
+        buf = c.dst_buf;
+        goff = c.dst_group_offset;
+        groups = (c.cout + 7) / 8;
+    }
+    if (kind) *kind = (int32_t)s.kind;
+    if (out_buffer) *out_buffer = buf;
+    if (out_group_offset) *out_group_offset = goff;
+    if (out_groups) *out_groups = groups;
+    if (name) std::memcpy(name, s.name, 32);
+    return ANX_OK;
+}
+
+anx_status anx_engine_run_steps(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h,
+                                int32_t w, void *workspace, size_t ws_bytes, void *stream, int32_t first,
+                                int32_t last) {
+    anx_status st = check_forward_args(e, in, out, n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    if (first < 0 || last > (int)e->steps.size() || first > last) return e->fail(ANX_ERR_BAD_ARG, "bad step range");
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    if (first == 0 && p->stats_bytes)
+        ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes,
+                                    static_cast<cudaStream_t>(stream)));
+    for (int i = first; i < last; ++i) {
+        st = launch_step(e, *p, e->steps[i], in, out, static_cast<cudaStream_t>(stream));
         if (st != ANX_OK) return st;
     }
     return ANX_OK;

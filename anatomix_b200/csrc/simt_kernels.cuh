@@ -18,7 +18,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (
 template <int COUT, int ZT>
 __global__ void __launch_bounds__(256, 2)
 stem_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, int cin, int N, int D, int H, int W,
-                 Epilogue ep) {
+                 int z_halo, Epilogue ep) {
     extern __shared__ float sw[];   // [cin][27][COUT]
     for (int i = threadIdx.x; i < cin * 27 * COUT; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
@@ -28,7 +28,9 @@ stem_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, int 
     const int n = blockIdx.z / ztiles;
     const int z0 = (blockIdx.z - n * ztiles) * ZT;
     const bool valid = (x < W) && (y < H);       // no early exit: the statistics path shuffles across the warp
-    const size_t plane = (size_t)D * H * W;
+    // z_halo: the input carries one extra plane at each end of D (depth-slab mode: the
+    // neighbour slab's boundary plane, or the caller's reflect copy at a global face)
+    const size_t plane = (size_t)(D + 2 * z_halo) * H * W;
     float acc[ZT][COUT];
 #pragma unroll
     for (int o = 0; o < ZT; ++o)
@@ -51,7 +53,7 @@ stem_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, int 
 #pragma unroll
                 for (int pz = 0; pz < ZT + 2; ++pz) {
                     int zz = z0 + pz - 1;                          // beyond D only for masked outputs
-                    zz = reflect_idx(zz < D ? zz : D, D);
+                    zz = z_halo ? (zz < D ? zz + 1 : D + 1) : reflect_idx(zz < D ? zz : D, D);
                     a[pz] = __ldg(col + (size_t)zz * H * W);
                 }
 #pragma unroll

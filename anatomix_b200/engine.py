@@ -179,6 +179,26 @@ class Engine:
         raw = names.raw
         return [(raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), ms[i]) for i in range(cnt.value)]
 
+    def step_table(self):
+        """[(kind, out_buffer, out_group_offset, out_groups, name)] per launch of a forward."""
+        out = []
+        for i in range(self.lib.anx_engine_num_steps(self._h)):
+            v = [C.c_int32() for _ in range(4)]
+            name = C.create_string_buffer(32)
+            self._check(self.lib.anx_engine_step_info(self._h, i, *[C.byref(x) for x in v], name))
+            out.append(tuple(x.value for x in v) + (name.value.decode(),))
+        return out
+
+    def run_steps(self, x: torch.Tensor, out: torch.Tensor, first: int, last: int):
+        """Runs launches [first, last) of the forward program (see anx_engine_run_steps).
+        ``x`` / ``out`` are the same tensors for every call of one forward."""
+        n, d, h, w = out.shape[0], out.shape[2], out.shape[3], out.shape[4]
+        ws = self.workspace(n, d, h, w)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_run_steps(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, first, last))
+
     def buffer_table(self, n, d, h, w):
         """[(offset, bytes, level, groups)] of the workspace's activation buffers."""
         out = []

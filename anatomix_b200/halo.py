@@ -1,0 +1,91 @@
+"""Depth-halo spatial partition: ONE oversized volume split along depth over the
+GPUs of a box (BASELINE config 5).
+
+Each rank owns a slab of ``D / world`` planes (boundaries multiples of
+``2**num_downs`` so pooling and nearest upsampling stay local at every level) and
+runs the ordinary engine on it, launch by launch.  After every launch that
+produces an activation tensor, neighbouring ranks swap ONE boundary plane of that
+tensor: my first interior plane goes into the upper shell plane of rank-1, my
+last interior plane into the lower shell plane of rank+1.  The engine's buffers
+already carry a one-voxel shell for reflect padding, so a received neighbour
+plane simply replaces the mirror copy at an interior slab face and every kernel
+runs unchanged; reflect padding survives only at the two global faces.  The
+network input is handed over with the neighbour planes attached
+(ANX_FLAG_DEPTH_HALO_INPUT).
+
+Supported: BatchNorm-eval / no-norm networks with nearest upsampling (the released
+6M model).  InstanceNorm would additionally need an all-reduce of the per-layer
+statistics, trilinear upsampling a low-resolution halo read.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .dist import exchange_halo_planes, slab_bounds
+from .engine import Engine
+
+
+def slab_input_with_halo(volume: torch.Tensor, z_lo: int, z_hi: int) -> torch.Tensor:
+    """``volume[:, :, z_lo-1 : z_hi+1]`` with reflect copies where the slab touches a
+    global face (plane -1 -> plane 1, plane D -> plane D-2)."""
+    depth = volume.shape[2]
+    idx = [z_lo - 1 if z_lo > 0 else 1] + list(range(z_lo, z_hi)) + [z_hi if z_hi < depth else depth - 2]
+    return volume.index_select(2, torch.tensor(idx, device=volume.device)).contiguous()
+
+
+class DepthSlabExtractor:
+    """Feature extraction of one ``[1, C, D, H, W]`` volume with D split over the
+    ranks of ``group``.  Every rank passes the same full volume (host or device
+    tensor) and gets its own slab of features, or the whole feature volume with
+    ``gather=True``."""
+
+    def __init__(self, cfg: dict, state: dict, device, group: Optional[dist.ProcessGroup] = None):
+        if cfg.get("norm", "batch") not in ("batch", "none") or cfg.get("interp", "nearest") != "nearest":
+            raise NotImplementedError("depth-slab mode covers BatchNorm-eval / nearest-upsampling networks")
+        self.cfg = cfg
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.engine = Engine(cfg, device, flags=_lib.FLAG_DEPTH_HALO_INPUT)
+        self.engine.load_state(state)
+        self.steps = self.engine.step_table()
+
+    def _exchange(self, ws, table, buf, goff, groups, n, d, h, w):
+        off, nbytes, level, gtot = table[buf]
+        dl, hl, wl = d >> level, h >> level, w >> level
+        plane = (hl + 2) * (wl + 2) * 16
+        view = ws[off:off + n * gtot * (dl + 2) * plane].view(n, gtot, dl + 2, plane)[:, goff:goff + groups]
+        lo_out, hi_out = view[:, :, 1].contiguous(), view[:, :, dl].contiguous()
+        lo_in, hi_in = torch.empty_like(lo_out), torch.empty_like(hi_out)
+        exchange_halo_planes(lo_out, hi_out, lo_in, hi_in, self.rank, self.world, self.group)
+        if self.rank > 0:
+            view[:, :, 0] = lo_in
+        if self.rank < self.world - 1:
+            view[:, :, dl + 1] = hi_in
+
+    @torch.no_grad()
+    def extract(self, volume: torch.Tensor, gather: bool = False) -> torch.Tensor:
+        n, _, depth, h, w = volume.shape
+        z_lo, z_hi = slab_bounds(depth, self.world, self.cfg["num_downs"])[self.rank]
+        d = z_hi - z_lo
+        x = slab_input_with_halo(volume, z_lo, z_hi).to(self.engine.device, torch.float32)
+        out = torch.empty((n, self.cfg["output_nc"], d, h, w), dtype=torch.float32, device=self.engine.device)
+        ws = self.engine.workspace(n, d, h, w)
+        table = self.engine.buffer_table(n, d, h, w)
+        for i, (kind, buf, goff, groups, name) in enumerate(self.steps):
+            self.engine.run_steps(x, out, i, i + 1)
+            if buf >= 0 and self.world > 1:
+                self._exchange(ws, table, buf, goff, groups, n, d, h, w)
+        if not gather or self.world == 1:
+            return out
+        # slabs have equal depth unless depth/unit is not a multiple of world: gather plane-major, then permute back
+        sizes = [b[1] - b[0] for b in slab_bounds(depth, self.world, self.cfg["num_downs"])]
+        if len(set(sizes)) != 1:
+            raise NotImplementedError("gather with unequal slabs")
+        pieces = [torch.empty_like(out) for _ in range(self.world)]
+        dist.all_gather(pieces, out, group=self.group)
+        return torch.cat(pieces, dim=2)

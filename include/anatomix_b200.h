@@ -74,6 +74,10 @@ typedef struct anx_unet_desc {
  * extra mantissa bits are needed through 24 normalised layers). */
 #define ANX_FLAG_STORE_FP16 2u
 #define ANX_FLAG_STORE_BF16 4u
+/* Depth-slab mode (one oversized volume split along D over several GPUs): the input
+ * tensor is [N, C, D+2, H, W] with one extra plane at each end of D (the neighbouring
+ * slab's boundary plane, or the caller's reflect copy at a global face). */
+#define ANX_FLAG_DEPTH_HALO_INPUT 8u
 
 /* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
  * device constants; no parameters yet. */
@@ -113,6 +117,21 @@ size_t anx_engine_workspace_bytes(const anx_engine *engine, int32_t n, int32_t d
 anx_status anx_engine_forward(anx_engine *engine, const float *in_ncdhw, float *out_ncdhw,
                               int32_t n, int32_t d, int32_t h, int32_t w,
                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* Step-wise execution, for callers that must act between layers (the depth-slab
+ * partition exchanges one halo plane with its neighbours after every producer).
+ * A step is one kernel launch of the forward; `anx_engine_step_info` names the
+ * activation buffer (index into anx_engine_buffer_info, -1 = network output) and the
+ * 8-channel group range the step writes.  `anx_engine_run_steps` runs steps
+ * [first, last) of the same program `anx_engine_forward` runs in one go. */
+int32_t anx_engine_num_steps(const anx_engine *engine);
+anx_status anx_engine_step_info(const anx_engine *engine, int32_t step, int32_t *kind,
+                                int32_t *out_buffer, int32_t *out_group_offset,
+                                int32_t *out_groups, char name[32]);
+anx_status anx_engine_run_steps(anx_engine *engine, const float *in_ncdhw, float *out_ncdhw,
+                                int32_t n, int32_t d, int32_t h, int32_t w,
+                                void *workspace, size_t workspace_bytes, void *stream,
+                                int32_t first_step, int32_t last_step);
 
 /* Same call for HOST buffers (pinned memory recommended): copies the input to
  * `dev_in`, runs the forward, copies `dev_out` back, all queued on `stream`.

@@ -1,0 +1,66 @@
+"""Two-GPU paths (NCCL): batch-sharded extraction with the feature all-gather and the
+depth-halo partition of one volume, each against the single-GPU engine.  Skipped on
+boxes with fewer than two GPUs (run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import CFG_6M, GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _state():
+    z = np.load(os.path.join(GOLDEN, "anatomix_6m_state.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from anatomix_b200.dist import ShardedExtractor
+        from anatomix_b200.engine import Engine
+        from anatomix_b200.halo import DepthSlabExtractor
+        state = _state()
+        eng = Engine(CFG_6M, dev)
+        eng.load_state(state)
+
+        # (1) batch sharding + all-gather of the 16-channel features
+        batch = torch.rand(4, 1, 32, 32, 32, generator=torch.Generator().manual_seed(3))
+        ex = ShardedExtractor(lambda t: eng.forward(t.to(dev)), 16)
+        full = ex.extract(batch.to(dev), gather=True)
+        ref = eng.forward(batch.to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(full, ref), "gathered features differ from the single-GPU result"
+
+        # (2) one volume, depth split in two slabs of 32 planes with per-layer halo planes
+        vol = torch.rand(1, 1, 64, 32, 48, generator=torch.Generator().manual_seed(4))
+        slab = DepthSlabExtractor(CFG_6M, state, dev)
+        got = slab.extract(vol, gather=True)
+        want = eng.forward(vol.to(dev))
+        torch.cuda.synchronize()
+        err = (got - want).abs().max().item()
+        rel = ((got - want).norm() / want.norm()).item()
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(f"{err} {rel}\n")
+        assert rel < 1e-3, f"depth-slab result differs from single-GPU: max abs {err}, rel-L2 {rel}"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharding_and_depth_halo(tmp_path):
+    port = 29700 + os.getpid() % 1000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        print(open(tmp_path / f"rank{r}.txt").read())
