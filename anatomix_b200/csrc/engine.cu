@@ -19,6 +19,7 @@
 #include "../../include/anatomix_b200.h"
 #include "conv_umma.cuh"
 #include "simt_kernels.cuh"
+#include "stem_umma.cuh"
 
 using namespace anx;
 
@@ -87,7 +88,8 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     int n_splits = 1, ncols_split = 0;        // Cout > 256: channel splits of 256 handled by different CTAs
     bool inorm = false;                       // followed by InstanceNorm: raw output + statistics
     size_t stats_index = 0;                   // first double of this conv's [N][ncols][2] block, per sample-channel
-    void *d_wpack = nullptr;  // bf16 slabs (tensor-core convs) or fp32 [cin][27][cout] (stem)
+    void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
+    void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
     float *d_bias = nullptr;  // [ncols]
     size_t wpack_bytes = 0;
 };
@@ -413,6 +415,46 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
     case STEP_STEM: {
         const ConvLayer &c = e->convs[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out);
+        const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
+        if (!force_simt && c.d_wstem && p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+            !getenv("ANX_SIMT_STEM")) {
+            // tensor-core stem: per-call tensor map over the caller's fp32 input
+            EncodeTiledFn encode = load_encode_tiled();
+            StemGeom g{};
+            g.N = p.N; g.D = p.D; g.H = p.H; g.W = p.W; g.cin = c.cin;
+            g.ncols = c.ncols;
+            g.kq = (9 * c.cin + 15) / 16;
+            g.bz = std::min(std::max(1, std::min(8, 256 / c.ncols)), p.D);
+            g.acc_stages = 2;
+            int cols = 32;
+            while (cols < g.acc_stages * g.bz * g.ncols) cols *= 2;
+            g.tmem_cols = cols;
+            g.z_halo = zh0;
+            if (const char *ds = getenv("ANX_STEM_SHIFT")) g.dbg_shift = atoi(ds);
+            g.tiles_x = (p.W + TILE_X - 1) / TILE_X;
+            g.tiles_y = (p.H + TILE_Y - 1) / TILE_Y;
+            g.tiles_z = (p.D + g.bz - 1) / g.bz;
+            g.tiles_per_sample = g.tiles_x * g.tiles_y * g.tiles_z;
+            g.total_tiles = g.tiles_per_sample * p.N;
+            g.brick_bytes = (uint32_t)(c.cin * (g.bz + 2) * HALO_Y * STEM_BRICK_X * 4);
+            g.a_tile_bytes = (uint32_t)(g.kq * 2 * 128 * 16);
+            g.b_bytes = (uint32_t)(g.kq * 2 * 3 * g.ncols * 16);
+            g.smem_bytes = 2 * ((g.brick_bytes + 127) & ~127u) + STEM_A_SLOTS * 2 * g.a_tile_bytes + 2 * g.b_bytes +
+                           (uint32_t)sizeof(StemShared);
+            CUtensorMap tm;
+            cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)(p.D + 2 * zh0), (cuuint64_t)p.N * c.cin};
+            cuuint64_t strides[3] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4,
+                                     (cuuint64_t)p.W * p.H * (p.D + 2 * zh0) * 4};
+            cuuint32_t box[4] = {STEM_BRICK_X, HALO_Y, (cuuint32_t)(g.bz + 2), (cuuint32_t)c.cin};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(in), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return e->fail(ANX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the stem input", (int)r);
+            const int grid = std::min(g.total_tiles, e->num_sms);
+            stem_umma_kernel<<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
+            break;
+        }
         const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
         const float *wp = (const float *)c.d_wpack;
         auto grid_of = [&](int zt) { return dim3((p.W + 31) / 32, (p.H + 7) / 8, p.N * ((p.D + zt - 1) / zt)); };
@@ -560,6 +602,8 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (err != cudaSuccess) {
         delete e;
         return ANX_ERR_CUDA;
@@ -572,6 +616,7 @@ void anx_engine_destroy(anx_engine *e) {
     if (!e) return;
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
+        if (c.d_wstem) cudaFree(c.d_wstem);
         if (c.d_bias) cudaFree(c.d_bias);
     }
     delete e;
@@ -638,6 +683,30 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
         c.wpack_bytes = pk.size() * sizeof(float);
         ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
         ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
+        if (9 * c.cin <= 16 * STEM_MAX_KQ && 3 * c.ncols <= 256) {
+            // tensor-core stem: K index = ci*9 + (ky*3+kx), rows = (dz=+1 | 0 | -1) x ncols, w = hi + lo in bf16
+            const int kq = (9 * c.cin + 15) / 16, R = 3 * c.ncols;
+            const size_t half_img = (size_t)kq * 2 * R * 8;
+            std::vector<uint16_t> img(2 * half_img, 0);
+            for (int o = 0; o < c.cout; ++o)
+                for (int i = 0; i < c.cin; ++i)
+                    for (int kz = 0; kz < 3; ++kz)
+                        for (int t = 0; t < 9; ++t) {
+                            const float v = hw[((size_t)o * c.cin + i) * 27 + kz * 9 + t] * scale[o];
+                            const uint16_t hi = f32_to_bf16_rne(v);
+                            uint32_t hb32 = (uint32_t)hi << 16;
+                            float hf;
+                            std::memcpy(&hf, &hb32, 4);
+                            const uint16_t lo = f32_to_bf16_rne(v - hf);
+                            const int k = i * 9 + t, row = (2 - kz) * c.ncols + o;
+                            const size_t idx = ((size_t)((k / 16) * 2 + (k % 16) / 8) * R + row) * 8 + k % 8;
+                            img[idx] = hi;
+                            img[half_img + idx] = lo;
+                        }
+            if (c.d_wstem) { cudaFree(c.d_wstem); c.d_wstem = nullptr; }
+            ANX_CUDA(e, cudaMalloc(&c.d_wstem, img.size() * 2));
+            ANX_CUDA(e, cudaMemcpy(c.d_wstem, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        }
     } else {
         // 16-bit slabs [split][chunk][group][tap(ky,kx)][kchunk][row][8]; folded rows = (dz=+1 | 0 | -1) x ncols
         const int W = c.ncols_split;
