@@ -272,11 +272,21 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         } else {
                             store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, y, x, q0, q1);
                         }
-                    } else {
+                    } else if (ep.n_peers == 0) {
                         float *o = fbase + (size_t)(cb * 16) * vol + (size_t)b * Hh * Ww;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                    } else {
+                        // fused all-gather: the same values go to every rank's gather buffer over NVLink
+                        const size_t off = ((size_t)(ep.sample_offset + t.n) * ep.cout + c0) * vol +
+                                           ((size_t)z * Hh + y) * Ww + x;
+                        for (int pr = 0; pr < ep.n_peers; ++pr) {
+                            float *o = ep.out_peers[pr] + off;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                        }
                     }
                 }
                 if (ep.stats) {   // whole warp converged here: the b loop has a warp-uniform trip count

@@ -106,6 +106,11 @@ struct Step {
     char name[32];
 };
 
+struct GatherArgs {           // fused all-gather destinations of the final conv (one forward call)
+    float *peers[8] = {nullptr};
+    int n_peers = 0, sample_offset = 0;
+};
+
 struct ShapePlan {            // everything that depends on (N, D, H, W, workspace)
     int N = 0, D = 0, H = 0, W = 0;
     void *workspace = nullptr;
@@ -373,8 +378,14 @@ anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, 
     return ANX_OK;
 }
 
-Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer &c, float *out) {
+Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer &c, float *out,
+                       const GatherArgs *ga = nullptr) {
     Epilogue ep{};
+    if (ga && c.is_final) {
+        for (int i = 0; i < ga->n_peers; ++i) ep.out_peers[i] = ga->peers[i];
+        ep.n_peers = ga->n_peers;
+        ep.sample_offset = ga->sample_offset;
+    }
     ep.cout = c.cout;
     ep.bias = c.d_bias;
     // with InstanceNorm the conv stores its raw output; the activation runs after the normalisation
@@ -409,7 +420,7 @@ int grid_for(size_t work_items, int threads, int num_sms, int waves) {
 }
 
 anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const float *in, float *out,
-                       cudaStream_t st) {
+                       cudaStream_t st, const GatherArgs *ga = nullptr) {
     const bool force_simt = (e->desc.flags & ANX_FLAG_FORCE_SIMT) != 0;
     switch (s.kind) {
     case STEP_STEM: {
@@ -474,7 +485,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
     case STEP_CONV: {
         const ConvLayer &c = e->convs[s.conv];
         const ConvGeom &g = p.geoms[s.conv];
-        Epilogue ep = make_epilogue(e, p, c, out);
+        Epilogue ep = make_epilogue(e, p, c, out, ga);
         if (force_simt) {
             ActView src = view_of(e, p, c.src_buf, 0);
             const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
@@ -820,6 +831,34 @@ anx_status anx_engine_run_steps(anx_engine *e, const float *in, float *out, int3
                                     static_cast<cudaStream_t>(stream)));
     for (int i = first; i < last; ++i) {
         st = launch_step(e, *p, e->steps[i], in, out, static_cast<cudaStream_t>(stream));
+        if (st != ANX_OK) return st;
+    }
+    return ANX_OK;
+}
+
+anx_status anx_engine_forward_allgather(anx_engine *e, const float *in, float *const *out_peers, int32_t world,
+                                        int32_t rank, int32_t n, int32_t d, int32_t h, int32_t w, void *workspace,
+                                        size_t ws_bytes, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (!out_peers || world < 1 || world > 8 || rank < 0 || rank >= world)
+        return e->fail(ANX_ERR_BAD_ARG, "bad peer list (world %d, rank %d; at most 8 peers)", world, rank);
+    for (int i = 0; i < world; ++i)
+        if (!out_peers[i]) return e->fail(ANX_ERR_BAD_ARG, "null gather buffer for peer %d", i);
+    anx_status st = check_forward_args(e, in, out_peers[rank], n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    GatherArgs ga;
+    for (int i = 0; i < world; ++i) ga.peers[i] = out_peers[i];
+    ga.n_peers = world;
+    ga.sample_offset = rank * n;
+    if (p->stats_bytes)
+        ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes,
+                                    static_cast<cudaStream_t>(stream)));
+    for (auto &s : e->steps) {
+        st = launch_step(e, *p, s, in, out_peers[rank], static_cast<cudaStream_t>(stream), &ga);
         if (st != ANX_OK) return st;
     }
     return ANX_OK;

@@ -129,10 +129,15 @@ __device__ __forceinline__ void epilogue_store16(const Epilogue &ep, int n, int 
         store_padded_groups(ep.dst, n, 2 * cb, ngroups, z, y, x, pack_x8(v, ep.dt), pack_x8(v + 8, ep.dt));
     } else {
         const size_t plane = (size_t)ep.dst.D * ep.dst.H * ep.dst.W;
-        float *o = ep.out_f32 + ((size_t)n * ep.cout + c0) * plane + ((size_t)z * ep.dst.H + y) * ep.dst.W + x;
+        const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
+        for (int pr = 0; pr < targets; ++pr) {
+            float *base = ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32;
+            const int ns = ep.n_peers > 0 ? ep.sample_offset + n : n;
+            float *o = base + ((size_t)ns * ep.cout + c0) * plane + ((size_t)z * ep.dst.H + y) * ep.dst.W + x;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c0 + i < ep.cout) o[(size_t)i * plane] = v[i];
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < ep.cout) o[(size_t)i * plane] = v[i];
+        }
     }
 }
 

@@ -54,6 +54,12 @@ struct Epilogue {
     int dt;                 // StoreType of dst
     double *stats;          // instance-norm sums [N][cout_padded][2] (sum, sum of squares) or nullptr
     int stats_stride;       // cout rounded up to 16 (channels per sample in `stats`)
+    // Fused feature all-gather (OUT_NCDHW_F32 only): when n_peers > 0 the output of local sample n is
+    // stored into EVERY peer's gather buffer at sample index sample_offset + n (peer pointers are
+    // NVLink-mapped device addresses; out_f32 is ignored).
+    float *out_peers[8];
+    int n_peers;
+    int sample_offset;
 };
 
 // tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),

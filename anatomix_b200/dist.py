@@ -86,6 +86,42 @@ class ShardedExtractor:
         return full
 
 
+class FusedGatherExtractor:
+    """Batch-sharded extraction where the all-gather is fused into the last conv:
+    its epilogue stores every output tile into all ranks' gather buffers over NVLink
+    (peer pointers from torch symmetric memory), so no separate collective runs.
+
+    ``extract(batch_shard)`` takes this rank's ``[n, C_in, D, H, W]`` CUDA shard (equal
+    ``n`` on every rank) and returns the full ``[world*n, C_out, D, H, W]`` tensor,
+    which lives in symmetric memory and is overwritten by the next call."""
+
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem
+        self.engine = engine
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("at most 8 peers (one NVSwitch box)")
+        self._buf = None
+        self._hdl = None
+
+    def _buffers(self, shape):
+        if self._buf is None or tuple(self._buf.shape) != tuple(shape):
+            self._buf = self._symm.empty(shape, dtype=torch.float32, device=self.engine.device)
+            self._hdl = self._symm.rendezvous(self._buf, self.group)
+        return self._buf, self._hdl
+
+    def extract(self, shard: torch.Tensor) -> torch.Tensor:
+        n, _, d, h, w = shard.shape
+        buf, hdl = self._buffers((self.world * n, self.engine.output_nc, d, h, w))
+        hdl.barrier()                                   # peers are done reading the previous result
+        self.engine.forward_allgather(shard, list(hdl.buffer_ptrs), self.rank)
+        hdl.barrier()                                   # every rank's stores have landed everywhere
+        return buf
+
+
 # ------------------------------------------------------------------ depth slabs
 def slab_bounds(depth: int, world: int, num_downs: int) -> List[Tuple[int, int]]:
     """Depth ranges [z_lo, z_hi) per rank for one volume of ``depth`` planes.

@@ -150,6 +150,20 @@ class Engine:
                 self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream))
         return out
 
+    def forward_allgather(self, x: torch.Tensor, peer_ptrs, rank: int):
+        """Forward whose last conv stores into every rank's gather buffer (see
+        anx_engine_forward_allgather).  ``peer_ptrs``: device pointers (ints) of the
+        ranks' [world*n, C, D, H, W] fp32 buffers, NVLink-mapped into this process."""
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_allgather(
+                self._h, x.data_ptr(), arr, world, rank, n, d, h, w, ws.data_ptr(), ws.numel(), stream))
+
     def forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
                      dev_out: torch.Tensor):
         """End-to-end call on (pinned) host buffers; see anx_engine_forward_host."""

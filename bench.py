@@ -232,6 +232,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allgather = {"ms": t.item(), "bytes_per_rank": out.numel() * 4,
                      "volumes_per_s_with_gather": world * B / ((ms / args.steps + t.item()) / 1e3)}
+        # the same gather fused into the last conv (epilogue stores into every peer's buffer over NVLink)
+        try:
+            from anatomix_b200.dist import FusedGatherExtractor
+            fused = FusedGatherExtractor(eng)
+            for i in range(2):
+                fused.extract(xs[i % n_in])
+            barrier()
+            ev0.record()
+            for i in range(args.steps):
+                fused.extract(xs[i % n_in])
+            ev1.record()
+            barrier()
+            tf = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            allgather["fused_ms_per_step"] = tf.item() / args.steps
+            allgather["volumes_per_s_fused_gather"] = world * B * args.steps / (tf.item() / 1e3)
+        except Exception as ex:          # symmetric memory unavailable on this box
+            allgather["fused_error"] = str(ex)[:200]
 
     if rank == 0:
         vols = world * B * args.steps

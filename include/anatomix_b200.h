@@ -133,6 +133,18 @@ anx_status anx_engine_run_steps(anx_engine *engine, const float *in_ncdhw, float
                                 void *workspace, size_t workspace_bytes, void *stream,
                                 int32_t first_step, int32_t last_step);
 
+/* Batch-sharded forward fused with the feature all-gather: the last conv's epilogue
+ * stores this rank's `n` output volumes straight into EVERY rank's gather buffer
+ * (`out_peers[r]` = NVLink-mapped device pointer to rank r's fp32
+ * [world*n, output_nc, D, H, W] buffer, e.g. from torch symmetric memory or CUDA IPC)
+ * at sample offset rank*n, so the transfer overlaps the conv tile by tile and no
+ * separate collective runs.  The caller synchronises the ranks afterwards (a
+ * barrier) before anyone reads its buffer.  At most 8 peers. */
+anx_status anx_engine_forward_allgather(anx_engine *engine, const float *in_ncdhw,
+                                        float *const *out_peers, int32_t world, int32_t rank,
+                                        int32_t n, int32_t d, int32_t h, int32_t w,
+                                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same call for HOST buffers (pinned memory recommended): copies the input to
  * `dev_in`, runs the forward, copies `dev_out` back, all queued on `stream`.
  * `dev_in` / `dev_out` are caller-owned device staging buffers of the input /

@@ -43,6 +43,17 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         assert torch.equal(full, ref), "gathered features differ from the single-GPU result"
 
+        # (1b) the same gather fused into the last conv's epilogue (peer stores over NVLink)
+        from anatomix_b200.dist import FusedGatherExtractor, shard_range
+        fused = FusedGatherExtractor(eng)
+        lo, hi = shard_range(4, world, rank)
+        got = fused.extract(batch[lo:hi].to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), "fused gather differs from the single-GPU result"
+        got2 = fused.extract(batch[lo:hi].to(dev) * 0.5)      # buffers are reused call after call
+        torch.cuda.synchronize()
+        assert torch.equal(got2, eng.forward(batch.to(dev) * 0.5))
+
         # (2) one volume, depth split in two slabs of 32 planes with per-layer halo planes
         vol = torch.rand(1, 1, 64, 32, 48, generator=torch.Generator().manual_seed(4))
         slab = DepthSlabExtractor(CFG_6M, state, dev)
