@@ -31,8 +31,7 @@
 // planes).  Rings: A bricks (stage = chunk), B weight slabs (stage = chunk x
 // dz-group), TMEM accumulator stages.  Persistent CTAs stride over tiles.
 #pragma once
-#include "epilogue.cuh"
-#include "ptx.cuh"
+#include "umma_epilogue.cuh"
 
 namespace anx {
 
@@ -217,83 +216,20 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         tc_fence_before();
         for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
 
-        const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
-        const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
-        const size_t gstride = (size_t)(Dd + 2) * plane;
-        const size_t vol = (size_t)Dd * Hh * Ww;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(g, tile);
             const uint32_t s = it % g.acc_stages;
-            const int chan0 = t.split * g.ncols;
             const int next_split = (tile + g.acc_stages * (int)gridDim.x) % g.n_splits;
-            const float *seed = sh->shift + next_split * g.ncols;
-            const int y = t.y0 + ly, x = t.x0 + lx;
-            const bool in_xy = (y < g.H) && (x < g.W);
-            const bool edge_xy = (x == 1) | (x == Ww - 2) | (y == 1) | (y == Hh - 2);
-            uint4 *pbase = nullptr;
-            float *fbase = nullptr;
-            if (ep.mode == OUT_PADDED_BF16)
-                pbase = ep.dst.at(t.n, chan0 >> 3, t.z0 + 1, y + 1, x + 1);
-            else
-                fbase = ep.out_f32 + ((size_t)t.n * ep.cout + chan0) * vol + ((size_t)t.z0 * Hh + y) * Ww + x;
+            EpiTile et;
+            et.n = t.n; et.z0 = t.z0; et.y = t.y0 + ly; et.x = t.x0 + lx;
+            et.chan0 = t.split * g.ncols;
+            et.in_xy = (et.y < g.H) && (et.x < g.W);
+            et.store = !(g.ablate & 2);
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
             tc_fence_after();
-            const uint32_t acc = lane_base + s * acc_cols;
-            for (int cb = 0; cb < chunks; ++cb) {
-                const int c0 = chan0 + cb * 16;
-                float s16[16], q16[16];
-                if (ep.stats) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
-                }
-                for (int b = half; b < g.bz; b += 2) {
-                    const int z = t.z0 + b;
-                    const bool ok = in_xy && z < g.D && !(g.ablate & 2);
-                    float v[16];
-                    __syncwarp();   // tcgen05.ld/st are warp-collective
-                    tmem_ld16(acc + b * g.ncols + cb * 16, v);
-                    tmem_st16(acc + b * g.ncols + cb * 16, seed + cb * 16);   // re-seed for the tile after next
-                    if (ep.stats && ok) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
-                    }
-                    if (!ok) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
-                    if (ep.mode == OUT_PADDED_BF16) {
-                        const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
-                        if (ngroups <= 0) continue;
-                        const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
-                        if (!edge_xy && z != 1 && z != Dd - 2) {
-                            uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
-                            *p = q0;
-                            if (ngroups > 1) p[gstride] = q1;
-                        } else {
-                            store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, y, x, q0, q1);
-                        }
-                    } else if (ep.n_peers == 0) {
-                        float *o = fbase + (size_t)(cb * 16) * vol + (size_t)b * Hh * Ww;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
-                    } else {
-                        // fused all-gather: the same values go to every rank's gather buffer over NVLink
-                        const size_t off = ((size_t)(ep.sample_offset + t.n) * ep.cout + c0) * vol +
-                                           ((size_t)z * Hh + y) * Ww + x;
-                        for (int pr = 0; pr < ep.n_peers; ++pr) {
-                            float *o = ep.out_peers[pr] + off;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
-                        }
-                    }
-                }
-                if (ep.stats) {   // whole warp converged here: the b loop has a warp-uniform trip count
-                    __syncwarp();
-                    warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2);
-                }
-            }
+            umma_epilogue_tile<1>(ep, et, lane_base + s * acc_cols, sh->shift + next_split * g.ncols, half, g.bz,
+                                  g.ncols, g.D);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);

@@ -206,6 +206,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Compiler-only dependency: keeps every use of r[0..15] behind the tcgen05.wait::ld that
+// precedes this call (the registers are written asynchronously by tcgen05.ld).
+__device__ __forceinline__ void tmem_ld_ready16(uint32_t *r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                      "+r"(r[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
     uint32_t z = 0;
     asm volatile(

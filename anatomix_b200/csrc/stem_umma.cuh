@@ -235,9 +235,6 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
         tc_fence_before();
         for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
 
-        const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
-        const size_t plane = (size_t)(Hh + 2) * (Ww + 2);
-        const size_t gstride = (size_t)(Dd + 2) * plane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const int n = tile / g.tiles_per_sample;
@@ -245,51 +242,15 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             const int tz = rr / (g.tiles_y * g.tiles_x);
             rr -= tz * g.tiles_y * g.tiles_x;
             const int ty = rr / g.tiles_x, tx = rr - ty * g.tiles_x;
-            const int z0 = tz * g.bz, y = ty * TILE_Y + ly, x = tx * TILE_X + lx;
             const uint32_t s = it % g.acc_stages;
-            const bool in_xy = (y < g.H) && (x < g.W);
-            const bool edge_xy = (x == 1) | (x == Ww - 2) | (y == 1) | (y == Hh - 2);
-            uint4 *pbase = ep.dst.at(n, 0, z0 + 1, y + 1, x + 1);
+            EpiTile et;
+            et.n = n; et.z0 = tz * g.bz; et.y = ty * TILE_Y + ly; et.x = tx * TILE_X + lx;
+            et.chan0 = 0;
+            et.in_xy = (et.y < g.H) && (et.x < g.W);
+            et.store = true;
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
-            const uint32_t acc = lane_base + s * acc_cols;
-            for (int cb = 0; cb < chunks; ++cb) {
-                const int c0 = cb * 16;
-                float s16[16], q16[16];
-                if (ep.stats) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
-                }
-                for (int b = half; b < g.bz; b += 2) {
-                    const int z = z0 + b;
-                    const bool ok = in_xy && z < g.D;
-                    float v[16];
-                    __syncwarp();
-                    tmem_ld16(acc + b * g.ncols + cb * 16, v);
-                    tmem_st16(acc + b * g.ncols + cb * 16, sh->shift + cb * 16);
-                    if (ep.stats && ok) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
-                    }
-                    if (!ok) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
-                    const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
-                    if (ngroups <= 0) continue;
-                    const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
-                    if (!edge_xy && z != 1 && z != Dd - 2) {
-                        uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
-                        *p = q0;
-                        if (ngroups > 1) p[gstride] = q1;
-                    } else {
-                        store_padded_groups(ep.dst, n, c0 >> 3, ngroups, z, y, x, q0, q1);
-                    }
-                }
-                if (ep.stats) {
-                    __syncwarp();
-                    warp_stats_add(s16, q16, ep.stats + ((size_t)n * ep.stats_stride + c0) * 2);
-                }
-            }
+            umma_epilogue_tile<1>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);

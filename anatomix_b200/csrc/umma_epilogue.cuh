@@ -1,0 +1,116 @@
+// Epilogue of one CTA tile, shared by the generic conv kernel and the stem kernel:
+// TMEM -> registers -> (instance-norm statistics) -> activation -> 16-bit pack ->
+// stores into the next layer's reflect-padded planar buffer (shell copies included),
+// or fp32 NCDHW / fused all-gather stores for the network output; and the re-seeding
+// of the drained accumulator columns with the per-channel shift.
+//
+// One call handles the planes b = half, half+2, ... of this warp's TMEM lane quadrant.
+// BATCH tcgen05.ld are issued back to back before the single wait, so the TMEM read
+// latency is paid once per batch instead of once per plane.
+#pragma once
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace anx {
+
+struct EpiTile {
+    int n, z0, y, x;        // sample, first output plane, this thread's voxel row / column
+    int chan0;              // first output channel of this CTA's channel split
+    bool in_xy;             // voxel inside the volume in y and x
+    bool store;             // false only in timing experiments
+};
+
+template <int BATCH>
+__device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
+                                                   const float *seed, int half, int bz, int ncols, int D) {
+    const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
+    const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
+    const size_t gstride = (size_t)(Dd + 2) * plane;
+    const size_t vol = (size_t)Dd * Hh * Ww;
+    const bool edge_xy = (t.x == 1) | (t.x == Ww - 2) | (t.y == 1) | (t.y == Hh - 2);
+    uint4 *pbase = nullptr;
+    float *fbase = nullptr;
+    if (ep.mode == OUT_PADDED_BF16)
+        pbase = ep.dst.at(t.n, t.chan0 >> 3, t.z0 + 1, t.y + 1, t.x + 1);
+    else
+        fbase = ep.out_f32 + ((size_t)t.n * ep.cout + t.chan0) * vol + ((size_t)t.z0 * Hh + t.y) * Ww + t.x;
+    const int chunks = ncols >> 4;
+    for (int cb = 0; cb < chunks; ++cb) {
+        const int c0 = t.chan0 + cb * 16;
+        float sd[16];   // this chunk's seed values (16-byte aligned in shared memory), reused for every plane
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 f = reinterpret_cast<const float4 *>(seed + cb * 16)[i];
+            sd[4 * i] = f.x; sd[4 * i + 1] = f.y; sd[4 * i + 2] = f.z; sd[4 * i + 3] = f.w;
+        }
+        float s16[16], q16[16];
+        if (ep.stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
+        }
+        for (int b0 = half; b0 < bz; b0 += 2 * BATCH) {
+            uint32_t r[BATCH][16];
+            __syncwarp();   // tcgen05.ld / st are warp-collective
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (b0 + 2 * k < bz) tmem_ld16_nowait(acc + (b0 + 2 * k) * ncols + cb * 16, r[k]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (b0 + 2 * k < bz) {
+                    tmem_ld_ready16(r[k]);
+                    tmem_st16(acc + (b0 + 2 * k) * ncols + cb * 16, sd);   // re-seed for a later tile
+                }
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int b = b0 + 2 * k;
+                if (b >= bz) break;
+                const int z = t.z0 + b;
+                const bool ok = t.in_xy && z < D && t.store;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k][i]);
+                if (ep.stats && ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
+                }
+                if (!ok) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
+                if (ep.mode == OUT_PADDED_BF16) {
+                    const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
+                    if (ngroups <= 0) continue;
+                    const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
+                    if (!edge_xy && z != 1 && z != Dd - 2) {
+                        uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
+                        *p = q0;
+                        if (ngroups > 1) p[gstride] = q1;
+                    } else {
+                        store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, t.y, t.x, q0, q1);
+                    }
+                } else if (ep.n_peers == 0) {
+                    float *o = fbase + (size_t)(cb * 16) * vol + (size_t)b * Hh * Ww;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                } else {
+                    // fused all-gather: the same values go to every rank's gather buffer over NVLink
+                    const size_t off = ((size_t)(ep.sample_offset + t.n) * ep.cout + c0) * vol +
+                                       ((size_t)z * Hh + t.y) * Ww + t.x;
+                    for (int pr = 0; pr < ep.n_peers; ++pr) {
+                        float *o = ep.out_peers[pr] + off;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                    }
+                }
+            }
+        }
+        if (ep.stats) {   // whole warp converged: the loops above have warp-uniform trip counts
+            __syncwarp();
+            warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2);
+        }
+    }
+}
+
+}   // namespace anx
