@@ -133,6 +133,10 @@ struct anx_engine {
     std::vector<Step> steps;
     std::mutex mu;
     std::vector<std::shared_ptr<ShapePlan>> plans;
+    // host-buffer pipeline (anx_engine_forward_host): copy streams and fork/join events
+    std::mutex host_mu;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in[8] = {nullptr}, ev_out[8] = {nullptr};
     mutable std::string last_error;
 
     anx_status fail(anx_status st, const char *fmt, ...) const {
@@ -625,6 +629,14 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
 
 void anx_engine_destroy(anx_engine *e) {
     if (!e) return;
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    for (int i = 0; i < 8; ++i) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
@@ -869,13 +881,46 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
                                    size_t ws_bytes, void *stream) {
     if (!e) return ANX_ERR_BAD_ARG;
     if (!in_host || !out_host || !dev_in || !dev_out) return e->fail(ANX_ERR_BAD_ARG, "null buffer");
+    if (!shape_ok(e, n, d, h, w)) return e->fail(ANX_ERR_BAD_SHAPE, "bad shape for the host-buffer forward");
+    std::lock_guard<std::mutex> lock(e->host_mu);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t vox = (size_t)n * d * h * w;
     ANX_CUDA(e, cudaSetDevice(e->desc.device));
-    ANX_CUDA(e, cudaMemcpyAsync(dev_in, in_host, vox * e->desc.input_nc * sizeof(float), cudaMemcpyHostToDevice, st));
-    anx_status r = anx_engine_forward(e, dev_in, dev_out, n, d, h, w, workspace, ws_bytes, stream);
-    if (r != ANX_OK) return r;
-    ANX_CUDA(e, cudaMemcpyAsync(out_host, dev_out, vox * e->desc.output_nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!e->h2d_stream) {
+        ANX_CUDA(e, cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+        ANX_CUDA(e, cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+        ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) {
+            ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+            ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    // Three-stage pipeline over chunks of the batch: the upload of chunk i+1 and the download of
+    // chunk i-1 run on their own streams while chunk i computes on the caller's stream.  The
+    // download (output_nc/input_nc times larger than the upload) is what bounds the call.
+    const int chunks = std::min(n, 4);
+    const size_t in_vol = (size_t)d * h * w * e->desc.input_nc, out_vol = (size_t)d * h * w * e->desc.output_nc;
+    ANX_CUDA(e, cudaEventRecord(e->ev_fork, st));
+    ANX_CUDA(e, cudaStreamWaitEvent(e->h2d_stream, e->ev_fork, 0));
+    ANX_CUDA(e, cudaStreamWaitEvent(e->d2h_stream, e->ev_fork, 0));
+    int lo = 0;
+    for (int i = 0; i < chunks; ++i) {
+        const int cnt = n / chunks + (i < n % chunks ? 1 : 0);
+        ANX_CUDA(e, cudaMemcpyAsync(dev_in + lo * in_vol, in_host + lo * in_vol, cnt * in_vol * sizeof(float),
+                                    cudaMemcpyHostToDevice, e->h2d_stream));
+        ANX_CUDA(e, cudaEventRecord(e->ev_in[i], e->h2d_stream));
+        ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_in[i], 0));
+        anx_status r = anx_engine_forward(e, dev_in + lo * in_vol, dev_out + lo * out_vol, cnt, d, h, w, workspace,
+                                          ws_bytes, stream);
+        if (r != ANX_OK) return r;
+        ANX_CUDA(e, cudaEventRecord(e->ev_out[i], st));
+        ANX_CUDA(e, cudaStreamWaitEvent(e->d2h_stream, e->ev_out[i], 0));
+        ANX_CUDA(e, cudaMemcpyAsync(out_host + lo * out_vol, dev_out + lo * out_vol, cnt * out_vol * sizeof(float),
+                                    cudaMemcpyDeviceToHost, e->d2h_stream));
+        lo += cnt;
+    }
+    ANX_CUDA(e, cudaEventRecord(e->ev_join, e->d2h_stream));
+    ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));   // the caller's stream completes after the last download
     return ANX_OK;
 }
 

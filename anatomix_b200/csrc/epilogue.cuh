@@ -75,17 +75,49 @@ __device__ __forceinline__ int mirror_target(int v, int S, int k) {
     return v == S - 2 ? S + 1 : -1;
 }
 
+// Shell copies of one 16-byte voxel group whose interior store went to `p`:
+// reflect padding puts x[1] into shell cell 0 (padded index v+1-2) and x[S-2] into
+// shell cell S+1 (padded index v+1+2), so every mirror copy sits at -2 / +2 cells
+// along each mirrored axis.  d* are those offsets in cells (0 = axis not mirrored);
+// valid for S >= 4 (a voxel then mirrors to at most one side per axis).
+__device__ __forceinline__ void store_mirrors(uint4 *p, const uint4 &q, int dz, int dy, int dx, size_t row,
+                                              size_t plane) {
+    if (dx) p[dx] = q;
+    if (dy) {
+        uint4 *py = p + (ptrdiff_t)dy * (ptrdiff_t)row;
+        *py = q;
+        if (dx) py[dx] = q;
+    }
+    if (dz) {
+        uint4 *pz = p + (ptrdiff_t)dz * (ptrdiff_t)plane;
+        *pz = q;
+        if (dx) pz[dx] = q;
+        if (dy) {
+            uint4 *pzy = pz + (ptrdiff_t)dy * (ptrdiff_t)row;
+            *pzy = q;
+            if (dx) pzy[dx] = q;
+        }
+    }
+}
+__device__ __forceinline__ int mirror_delta(int v, int S) { return v == 1 ? -2 : (v == S - 2 ? 2 : 0); }
+
 // Stores `ngroups` (1 or 2) packed 8-channel groups of voxel (n,z,y,x) starting at
 // group g0 into a padded planar buffer, including its reflect-shell copies.
 __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, int g0, int ngroups, int z, int y,
                                                     int x, const uint4 &q0, const uint4 &q1) {
-    const bool interior = (z != 1) & (z != dst.D - 2) & (y != 1) & (y != dst.H - 2) & (x != 1) & (x != dst.W - 2);
-    if (interior) {   // the common case
-        uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
+    const size_t row = (size_t)(dst.W + 2), plane = row * (dst.H + 2), gstride = plane * (dst.D + 2);
+    uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
+    if (dst.D >= 4 && dst.H >= 4 && dst.W >= 4) {
+        const int dz = mirror_delta(z, dst.D), dy = mirror_delta(y, dst.H), dx = mirror_delta(x, dst.W);
         *p = q0;
-        if (ngroups > 1) *dst.at(n, g0 + 1, z + 1, y + 1, x + 1) = q1;
+        if (ngroups > 1) p[gstride] = q1;
+        if (dz | dy | dx) {
+            store_mirrors(p, q0, dz, dy, dx, row, plane);
+            if (ngroups > 1) store_mirrors(p + gstride, q1, dz, dy, dx, row, plane);
+        }
         return;
     }
+    // tiny tensors (a size-2 or size-3 axis mirrors one voxel to both sides): generic loops
     for (int a = 0; a < 3; ++a) {
         const int zt = mirror_target(z, dst.D, a);
         if (zt < 0) continue;

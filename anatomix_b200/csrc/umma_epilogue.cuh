@@ -27,7 +27,9 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
-    const bool edge_xy = (t.x == 1) | (t.x == Ww - 2) | (t.y == 1) | (t.y == Hh - 2);
+    const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
+    const int mdx = mirror_delta(t.x, Ww), mdy = mirror_delta(t.y, Hh);
+    const size_t rowp = (size_t)(Ww + 2);
     uint4 *pbase = nullptr;
     float *fbase = nullptr;
     if (ep.mode == OUT_PADDED_BF16)
@@ -81,10 +83,15 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                     const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
                     if (ngroups <= 0) continue;
                     const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
-                    if (!edge_xy && z != 1 && z != Dd - 2) {
+                    if (big) {
                         uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
                         *p = q0;
                         if (ngroups > 1) p[gstride] = q1;
+                        const int mdz = mirror_delta(z, Dd);
+                        if (mdx | mdy | mdz) {   // shell copies: a few predicated stores, no loops
+                            store_mirrors(p, q0, mdz, mdy, mdx, rowp, plane);
+                            if (ngroups > 1) store_mirrors(p + gstride, q1, mdz, mdy, mdx, rowp, plane);
+                        }
                     } else {
                         store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, t.y, t.x, q0, q1);
                     }

@@ -279,6 +279,22 @@ def test_module_routes_to_engine_and_back(state_6m):
     assert list(m._anx_binding.engines) == [torch.device("cuda", 0)]
 
 
+def test_host_buffer_entry_point(state_6m):
+    """anx_engine_forward_host: pinned host buffers in and out, chunked upload / compute /
+    download pipeline; must equal the device-buffer forward bit for bit."""
+    eng = make_engine(CFG_6M, state_6m)
+    for n in (1, 3, 8):
+        x = rand_input((n, 1, 32, 32, 32), 20 + n)
+        xh = x.pin_memory()
+        yh = torch.empty((n, 16, 32, 32, 32), dtype=torch.float32).pin_memory()
+        dev_in = torch.empty((n, 1, 32, 32, 32), device="cuda")
+        dev_out = torch.empty((n, 16, 32, 32, 32), device="cuda")
+        eng.forward_host(xh, yh, dev_in, dev_out)
+        torch.cuda.synchronize()
+        want = eng.forward(x.cuda()).cpu()
+        assert torch.equal(yh, want), f"host-buffer forward differs at batch {n}"
+
+
 def test_errors_mirror_the_reference(state_6m):
     from anatomix_b200.engine import Engine, EngineError
     eng = make_engine(CFG_6M, state_6m)
