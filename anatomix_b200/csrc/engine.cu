@@ -467,7 +467,12 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return e->fail(ANX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the stem input", (int)r);
             const int grid = std::min(g.total_tiles, e->num_sms);
-            stem_umma_kernel<<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
+            if (g.kq == 1)
+                stem_umma_kernel<1><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
+            else if (g.kq == 2)
+                stem_umma_kernel<2><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
+            else
+                stem_umma_kernel<3><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
             break;
         }
         const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
@@ -618,7 +623,11 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        err = cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(stem_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (err != cudaSuccess) {
         delete e;
         return ANX_ERR_CUDA;

@@ -57,6 +57,14 @@ __device__ __forceinline__ int brick_reflect(int i, int lo, int hi) {   // lo/hi
     return i < lo ? 2 * lo - i : (i > hi ? 2 * hi - i : i);
 }
 
+// hi/lo split of two fp32 values into packed bf16 pairs: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split_hi_lo(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
+
+template <int KQ>   // K chunks of 16: 1 for Cin = 1, 2 for Cin = 2..3, 3 for Cin = 4
 __global__ void __launch_bounds__(STEM_THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, const uint8_t *__restrict__ wpack,
                  const Epilogue ep) {
@@ -142,7 +150,8 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 const uint32_t row0 = (uint32_t)(lo - (j - 2)) * g.ncols;
                 const uint32_t ah = (smem_u32(a_ring + (size_t)sa * 2 * g.a_tile_bytes) & 0x3FFFF) >> 4;
                 const uint32_t al = ah + (g.a_tile_bytes >> 4);
-                for (int kc = 0; kc < g.kq; ++kc) {
+#pragma unroll
+                for (int kc = 0; kc < KQ; ++kc) {
                     const uint32_t ao = kc * (2 * 128), bo = kc * (2 * R) + row0;   // 16 B units per K chunk of 16
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (ah + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (al + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
@@ -183,37 +192,33 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             for (int j = 0; j < planes; ++j, ++ka) {
                 const uint32_t sa = ka % STEM_A_SLOTS;
                 const int bzj = brick_reflect(min(j, zhi + 1), zlo, zhi);
-                float v[STEM_MAX_KQ * 16];
+                // K index = c*9 + (dy*3+dx); 16*KQ slots, unused ones are zero
+                float v[16 * KQ];
 #pragma unroll
-                for (int i = 0; i < STEM_MAX_KQ * 16; ++i) v[i] = 0.0f;
-                for (int c = 0; c < g.cin; ++c) {
-                    const float *pl = brick + ((size_t)(c * planes + bzj) * HALO_Y) * STEM_BRICK_X;
+                for (int i = 0; i < 16 * KQ; ++i) v[i] = 0.0f;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const float val = pl[by[t / 3] * STEM_BRICK_X + bx[t % 3]];
-                        // static indexing keeps v[] in registers: cin <= 4 unrolled by hand
-                        if (c == 0) v[t] = val;
-                        else if (c == 1) v[9 + t] = val;
-                        else if (c == 2) v[18 + t] = val;
-                        else v[27 + t] = val;
+                for (int c = 0; c < (16 * KQ) / 9; ++c) {
+                    if (c < g.cin) {
+                        const float *pl = brick + ((size_t)(c * planes + bzj) * HALO_Y) * STEM_BRICK_X;
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) v[c * 9 + t] = pl[by[t / 3] * STEM_BRICK_X + bx[t % 3]];
                     }
+                }
+                uint32_t hi[8 * KQ], lo[8 * KQ];
+#pragma unroll
+                for (int i = 0; i < 8 * KQ; ++i) {
+                    if (2 * i < 9 * ((16 * KQ) / 9)) split_hi_lo(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                    else { hi[i] = 0u; lo[i] = 0u; }
                 }
                 mbar_wait(&sh->empty_a[sa], ((ka / STEM_A_SLOTS) & 1) ^ 1, 16);
                 uint8_t *ah = a_ring + (size_t)sa * 2 * g.a_tile_bytes, *al = ah + g.a_tile_bytes;
 #pragma unroll
-                for (int h8 = 0; h8 < STEM_MAX_KQ * 2; ++h8) {
-                    if (h8 >= g.kq * 2) break;
-                    float hi8[8], lo8[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float x = v[h8 * 8 + e];
-                        const float xh = __bfloat162float(__float2bfloat16_rn(x));
-                        hi8[e] = xh;
-                        lo8[e] = x - xh;
-                    }
+                for (int h8 = 0; h8 < 2 * KQ; ++h8) {
                     // canonical K-major: [K half-chunk][row][8 elements], 16 B per row
-                    *reinterpret_cast<uint4 *>(ah + ((size_t)h8 * 128 + r) * 16) = pack_x8(hi8, DT_BF16);
-                    *reinterpret_cast<uint4 *>(al + ((size_t)h8 * 128 + r) * 16) = pack_x8(lo8, DT_BF16);
+                    *reinterpret_cast<uint4 *>(ah + ((size_t)h8 * 128 + r) * 16) =
+                        make_uint4(hi[4 * h8], hi[4 * h8 + 1], hi[4 * h8 + 2], hi[4 * h8 + 3]);
+                    *reinterpret_cast<uint4 *>(al + ((size_t)h8 * 128 + r) * 16) =
+                        make_uint4(lo[4 * h8], lo[4 * h8 + 1], lo[4 * h8 + 2], lo[4 * h8 + 3]);
                 }
                 fence_proxy_async();          // make the generic-proxy stores visible to the MMA
                 mbar_arrive(&sh->full_a[sa]);
