@@ -208,7 +208,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         // seed every accumulator stage with the per-channel shift of the tile that will use it
         for (int s = 0; s < g.acc_stages; ++s) {
             const int split = (blockIdx.x + s * (int)gridDim.x) % g.n_splits;
-            for (int b = half; b < g.bz; b += 2)
+            for (int b = plane_lo(half, g.bz); b < plane_hi(half, g.bz); ++b)
                 for (int cb = 0; cb < chunks; ++cb)
                     tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + split * g.ncols + cb * 16);
         }

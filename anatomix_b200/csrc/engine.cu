@@ -87,6 +87,7 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     int fold = 0, groups = 3;
     int n_splits = 1, ncols_split = 0;        // Cout > 256: channel splits of 256 handled by different CTAs
     bool inorm = false;                       // followed by InstanceNorm: raw output + statistics
+    int pool_dst_buf = -1;                    // >= 0: the following 2x2x2 pool may be fused into this conv's epilogue
     size_t stats_index = 0;                   // first double of this conv's [N][ncols][2] block, per sample-channel
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
@@ -223,8 +224,11 @@ void build_program(anx_engine *e) {
         add_conv(e, mi, i == 0 ? g : width[i - 1], width[i], i, false, false, cur, t, 0);
         add_conv(e, mi, width[i], width[i], i, false, false, t, cat[i], 0);
         int p = add_buffer(e, i + 1, width[i]);
+        if (!(d.flags & ANX_FLAG_FORCE_SIMT) && d.norm_kind != ANX_NORM_INSTANCE && !getenv("ANX_NO_POOL_FUSION"))
+            e->convs.back().pool_dst_buf = p;     // epilogue-fused when the tile shape allows (see make_geom)
         Step s{};
         s.kind = STEP_POOL;
+        s.conv = (int)e->convs.size() - 1;
         s.src_buf = cat[i];
         s.dst_buf = p;
         s.groups = width[i] / 8;
@@ -287,6 +291,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.acc_stages = 2;
     bz = std::min(bz, D);
     g.bz = bz;
+    g.fuse_pool = (c.pool_dst_buf >= 0 && bz % 4 == 0) ? 1 : 0;
     int cols = g.acc_stages * bz * g.ncols;
     int p2 = 32;
     while (p2 < cols) p2 *= 2;
@@ -383,8 +388,13 @@ anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, 
 }
 
 Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer &c, float *out,
-                       const GatherArgs *ga = nullptr) {
+                       const GatherArgs *ga = nullptr, const ConvGeom *g = nullptr) {
     Epilogue ep{};
+    ep.pool_kind = -1;
+    if (g && g->fuse_pool) {
+        ep.pool_kind = e->desc.pool_kind;
+        ep.pool_dst = view_of(e, p, c.pool_dst_buf, 0);
+    }
     if (ga && c.is_final) {
         for (int i = 0; i < ga->n_peers; ++i) ep.out_peers[i] = ga->peers[i];
         ep.n_peers = ga->n_peers;
@@ -494,7 +504,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
     case STEP_CONV: {
         const ConvLayer &c = e->convs[s.conv];
         const ConvGeom &g = p.geoms[s.conv];
-        Epilogue ep = make_epilogue(e, p, c, out, ga);
+        Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
         if (force_simt) {
             ActView src = view_of(e, p, c.src_buf, 0);
             const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
@@ -508,6 +518,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         break;
     }
     case STEP_POOL: {
+        if (!force_simt && p.geoms[s.conv].fuse_pool) return ANX_OK;   // already written by the conv's epilogue
         ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, 0);
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
         pool2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
@@ -795,7 +806,16 @@ int32_t anx_engine_num_buffers(const anx_engine *e) { return e ? (int32_t)e->buf
 
 int32_t anx_engine_launches_per_forward(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w) {
     if (!e || !shape_ok(e, n, d, h, w)) return -1;
-    return (int32_t)e->steps.size();
+    int32_t count = 0;
+    for (auto &s : e->steps) {
+        if (s.kind == STEP_POOL && !(e->desc.flags & ANX_FLAG_FORCE_SIMT)) {
+            const ConvLayer &c = e->convs[s.conv];
+            const int bz = std::min(std::max(1, std::min(8, 256 / c.ncols_split)), d >> c.level);
+            if (c.pool_dst_buf >= 0 && bz % 4 == 0) continue;   // fused into the producing conv
+        }
+        ++count;
+    }
+    return count;
 }
 
 anx_status anx_engine_forward(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h, int32_t w,

@@ -60,6 +60,11 @@ struct Epilogue {
     float *out_peers[8];
     int n_peers;
     int sample_offset;
+    // Fused 2x2x2 pooling (tensor-core kernel only): besides the full-resolution store, the epilogue
+    // reduces each 2x2x2 block (z pair in registers, y / x pairs by warp shuffles) and writes the
+    // pooled tensor with its shell.  pool_kind: -1 off, 0 max, 1 mean.
+    int pool_kind;
+    ActView pool_dst;
 };
 
 // tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),
@@ -90,6 +95,7 @@ struct ConvGeom {
     uint32_t b_stage_bytes; // 9 * 32 * R, R = rows per tap matrix
     uint32_t b_rows;        // R = fold ? 3*ncols : ncols
     uint32_t smem_bytes;
+    int fuse_pool;          // this launch also writes the pooled tensor (needs bz % 4 == 0)
     uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load
 };
 

@@ -234,7 +234,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks = g.ncols >> 4;
         for (int s = 0; s < g.acc_stages; ++s)
-            for (int b = half; b < g.bz; b += 2)
+            for (int b = plane_lo(half, g.bz); b < plane_hi(half, g.bz); ++b)
                 for (int cb = 0; cb < chunks; ++cb) tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + cb * 16);
         tmem_wait_st();
         tc_fence_before();

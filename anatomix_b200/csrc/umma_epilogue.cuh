@@ -20,6 +20,11 @@ struct EpiTile {
     bool store;             // false only in timing experiments
 };
 
+// Planes of a tile are split between the two warps of a TMEM lane quadrant in contiguous
+// halves: warp `half` owns [plane_lo, plane_hi).
+__device__ __forceinline__ int plane_lo(int half, int bz) { return half * ((bz + 1) >> 1); }
+__device__ __forceinline__ int plane_hi(int half, int bz) { return half ? bz : ((bz + 1) >> 1); }
+
 template <int BATCH>
 __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
                                                    const float *seed, int half, int bz, int ncols, int D) {
@@ -50,23 +55,85 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
         }
-        for (int b0 = half; b0 < bz; b0 += 2 * BATCH) {
+        const int b_end = plane_hi(half, bz);
+        if (ep.pool_kind >= 0) {
+            // ---- fused 2x2x2 pooling: planes in pairs (b, b+1); requires an even, pair-aligned plane range
+            const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
+            for (int b = plane_lo(half, bz); b < b_end; b += 2) {
+                uint32_t r0[16], r1[16];
+                __syncwarp();
+                tmem_ld16_nowait(acc + b * ncols + cb * 16, r0);
+                tmem_ld16_nowait(acc + (b + 1) * ncols + cb * 16, r1);
+                tmem_wait_ld();
+                tmem_ld_ready16(r0);
+                tmem_ld_ready16(r1);
+                tmem_st16(acc + b * ncols + cb * 16, sd);
+                tmem_st16(acc + (b + 1) * ncols + cb * 16, sd);
+                const int z = t.z0 + b;
+                const bool ok = t.in_xy && z < D && t.store;     // the pair is inside or outside together (even sizes)
+                float v0[16], v1[16], m[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v0[i] = activate(__uint_as_float(r0[i]), ep.act, ep.slope);
+                    v1[i] = activate(__uint_as_float(r1[i]), ep.act, ep.slope);
+                }
+                const uint4 a0 = pack_x8(v0, ep.dt), a1 = pack_x8(v0 + 8, ep.dt);
+                const uint4 c0q = pack_x8(v1, ep.dt), c1q = pack_x8(v1 + 8, ep.dt);
+                if (ok && ngroups > 0) {
+                    if (big) {
+                        uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
+                        p[0] = a0;
+                        p[plane] = c0q;
+                        if (ngroups > 1) { p[gstride] = a1; p[gstride + plane] = c1q; }
+                        const int mz0 = mirror_delta(z, Dd), mz1 = mirror_delta(z + 1, Dd);
+                        if (mdx | mdy | mz0) {
+                            store_mirrors(p, a0, mz0, mdy, mdx, rowp, plane);
+                            if (ngroups > 1) store_mirrors(p + gstride, a1, mz0, mdy, mdx, rowp, plane);
+                        }
+                        if (mdx | mdy | mz1) {
+                            store_mirrors(p + plane, c0q, mz1, mdy, mdx, rowp, plane);
+                            if (ngroups > 1) store_mirrors(p + gstride + plane, c1q, mz1, mdy, mdx, rowp, plane);
+                        }
+                    } else {
+                        store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, t.y, t.x, a0, a1);
+                        store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z + 1, t.y, t.x, c0q, c1q);
+                    }
+                }
+                // pool the STORED (rounded) values, as the reference pools the stored activation
+                unpack_x8(a0, v0, ep.dt); unpack_x8(a1, v0 + 8, ep.dt);
+                unpack_x8(c0q, v1, ep.dt); unpack_x8(c1q, v1 + 8, ep.dt);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a = ep.pool_kind == 0 ? fmaxf(v0[i], v1[i]) : v0[i] + v1[i];
+                    const float bx = __shfl_xor_sync(0xffffffffu, a, 1);       // x neighbour
+                    a = ep.pool_kind == 0 ? fmaxf(a, bx) : a + bx;
+                    const float by = __shfl_xor_sync(0xffffffffu, a, 8);       // y neighbour (rows are 8 lanes apart)
+                    a = ep.pool_kind == 0 ? fmaxf(a, by) : a + by;
+                    m[i] = ep.pool_kind == 0 ? a : a * 0.125f;
+                }
+                if (ok && ngroups > 0 && !((t.x | t.y) & 1))
+                    store_padded_groups(ep.pool_dst, t.n, c0 >> 3, ngroups, z >> 1, t.y >> 1, t.x >> 1, pack_x8(m, ep.dt),
+                                        pack_x8(m + 8, ep.dt));
+            }
+            continue;
+        }
+        for (int b0 = plane_lo(half, bz); b0 < b_end; b0 += BATCH) {
             uint32_t r[BATCH][16];
             __syncwarp();   // tcgen05.ld / st are warp-collective
 #pragma unroll
             for (int k = 0; k < BATCH; ++k)
-                if (b0 + 2 * k < bz) tmem_ld16_nowait(acc + (b0 + 2 * k) * ncols + cb * 16, r[k]);
+                if (b0 + k < b_end) tmem_ld16_nowait(acc + (b0 + k) * ncols + cb * 16, r[k]);
             tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < BATCH; ++k)
-                if (b0 + 2 * k < bz) {
+                if (b0 + k < b_end) {
                     tmem_ld_ready16(r[k]);
-                    tmem_st16(acc + (b0 + 2 * k) * ncols + cb * 16, sd);   // re-seed for a later tile
+                    tmem_st16(acc + (b0 + k) * ncols + cb * 16, sd);   // re-seed for a later tile
                 }
 #pragma unroll
             for (int k = 0; k < BATCH; ++k) {
-                const int b = b0 + 2 * k;
-                if (b >= bz) break;
+                const int b = b0 + k;
+                if (b >= b_end) break;
                 const int z = t.z0 + b;
                 const bool ok = t.in_xy && z < D && t.store;
                 float v[16];
