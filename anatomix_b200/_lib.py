@@ -22,6 +22,7 @@ FLAG_FORCE_SIMT = 1
 FLAG_STORE_FP16 = 2
 FLAG_STORE_BF16 = 4
 FLAG_DEPTH_HALO_INPUT = 8
+FLAG_NO_UPCONV = 16
 
 # every symbol include/anatomix_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -69,6 +69,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+// SEEDED: accumulators start from a stored partial-sum tensor (ep.seed_src) instead of the channel
+// shift -- the skip half of a decoder conv whose upsampled half was evaluated at low resolution.
+template <bool SEEDED>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g, const uint8_t *__restrict__ wpack,
                   const Epilogue ep) {
@@ -205,12 +208,35 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         const int ly = r >> 3, lx = r & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks = g.ncols >> 4;
-        // seed every accumulator stage with the per-channel shift of the tile that will use it
+        auto epi_tile_of = [&](int tile) {
+            const TileCoord t = decode_tile(g, tile);
+            EpiTile et;
+            et.n = t.n; et.z0 = t.z0; et.y = t.y0 + ly; et.x = t.x0 + lx;
+            et.chan0 = t.split * g.ncols;
+            et.in_xy = (et.y < g.H) && (et.x < g.W);
+            et.store = !(g.ablate & 2);
+            return et;
+        };
+        // seed every accumulator stage for the first tile that will use it
         for (int s = 0; s < g.acc_stages; ++s) {
-            const int split = (blockIdx.x + s * (int)gridDim.x) % g.n_splits;
-            for (int b = plane_lo(half, g.bz); b < plane_hi(half, g.bz); ++b)
-                for (int cb = 0; cb < chunks; ++cb)
-                    tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + split * g.ncols + cb * 16);
+            const int tile0 = blockIdx.x + s * (int)gridDim.x;
+            if (SEEDED) {
+                const bool valid = tile0 < g.total_tiles;
+                const EpiTile e0 = epi_tile_of(valid ? tile0 : 0);
+                for (int b = plane_lo(half, g.bz); b < plane_hi(half, g.bz); ++b) {
+                    uint4 q0, q1;
+                    float sv[16];
+                    load_seed16(ep, e0, valid, b, g.D, q0, q1);
+                    unpack_x8(q0, sv, ep.dt);
+                    unpack_x8(q1, sv + 8, ep.dt);
+                    tmem_st16(lane_base + s * acc_cols + b * g.ncols, sv);
+                }
+            } else {
+                const int split = tile0 % g.n_splits;
+                for (int b = plane_lo(half, g.bz); b < plane_hi(half, g.bz); ++b)
+                    for (int cb = 0; cb < chunks; ++cb)
+                        tmem_st16(lane_base + s * acc_cols + b * g.ncols + cb * 16, sh->shift + split * g.ncols + cb * 16);
+            }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -218,18 +244,16 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
 
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = decode_tile(g, tile);
+            const EpiTile et = epi_tile_of(tile);
             const uint32_t s = it % g.acc_stages;
-            const int next_split = (tile + g.acc_stages * (int)gridDim.x) % g.n_splits;
-            EpiTile et;
-            et.n = t.n; et.z0 = t.z0; et.y = t.y0 + ly; et.x = t.x0 + lx;
-            et.chan0 = t.split * g.ncols;
-            et.in_xy = (et.y < g.H) && (et.x < g.W);
-            et.store = !(g.ablate & 2);
+            const int next = tile + g.acc_stages * (int)gridDim.x;   // the tile that reuses this accumulator stage
+            const bool next_valid = SEEDED && next < g.total_tiles;
+            const EpiTile en = SEEDED ? epi_tile_of(next_valid ? next : tile) : et;
+            if (SEEDED) prefetch_seeds(ep, en, next_valid, half, g.bz, g.D);   // in flight during the wait
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
             tc_fence_after();
-            umma_epilogue_tile<1>(ep, et, lane_base + s * acc_cols, sh->shift + next_split * g.ncols, half, g.bz,
-                                  g.ncols, g.D);
+            umma_epilogue_tile<SEEDED>(ep, et, lane_base + s * acc_cols, sh->shift + (next % g.n_splits) * g.ncols, half,
+                                       g.bz, g.ncols, g.D, en, next_valid);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);

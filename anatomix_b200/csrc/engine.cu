@@ -88,6 +88,8 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     int n_splits = 1, ncols_split = 0;        // Cout > 256: channel splits of 256 handled by different CTAs
     bool inorm = false;                       // followed by InstanceNorm: raw output + statistics
     int pool_dst_buf = -1;                    // >= 0: the following 2x2x2 pool may be fused into this conv's epilogue
+    int d2s_cout = 0;                         // > 0: low-resolution half of a decoder conv (depth-to-space store)
+    int seed_buf = -1;                        // >= 0: skip half of that conv, accumulators seeded from this buffer
     size_t stats_index = 0;                   // first double of this conv's [N][ncols][2] block, per sample-channel
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
@@ -97,6 +99,15 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
 
 struct Buffer {               // padded planar activation buffer
     int level, groups;
+    int shell_rep = 0;        // producer writes replicate instead of reflect copies into the shell
+};
+
+// One nn.Conv3d of the reference's Sequential as the binding sees it (anx_engine_set_conv ordinal).
+// A decoder conv behind a nearest upsample may run as TWO launches (see build_program): conv_b >= 0.
+struct Logical {
+    int module_index, cin, cout;
+    bool has_norm;
+    int conv_a, conv_b;
 };
 
 struct Step {
@@ -130,6 +141,7 @@ struct anx_engine {
     int num_sms = 148;
     int max_smem = 0;
     std::vector<ConvLayer> convs;
+    std::vector<Logical> logical;
     std::vector<Buffer> bufs;
     std::vector<Step> steps;
     std::mutex mu;
@@ -162,7 +174,7 @@ struct anx_engine {
 namespace {
 
 int add_buffer(anx_engine *e, int level, int channels) {
-    e->bufs.push_back(Buffer{level, channels / 8});
+    e->bufs.push_back(Buffer{level, channels / 8, 0});
     return (int)e->bufs.size() - 1;
 }
 
@@ -190,6 +202,7 @@ void add_conv(anx_engine *e, int &module_index, int cin, int cout, int level, bo
     s.kind = stem ? STEP_STEM : STEP_CONV;
     s.conv = (int)e->convs.size();
     snprintf(s.name, sizeof s.name, "conv%d_%dto%d_L%d", c.module_index, cin, cout, level);
+    e->logical.push_back(Logical{c.module_index, cin, cout, c.has_norm, (int)e->convs.size(), -1});
     e->convs.push_back(c);
     e->steps.push_back(s);
     if (c.inorm) {   // normalise + activate in place once the whole tensor's statistics exist
@@ -244,7 +257,53 @@ void build_program(anx_engine *e) {
         add_conv(e, mi, width[nd], width[nd], nd, false, false, t, u, 0);
         cur = u;
     }
+    // Decoder level 0 behind a NEAREST upsample: conv(cat(skip, up(L))) = conv_skip(skip) + conv_up(up(L)).
+    // up(L) is piecewise constant, so conv_up(up(L)) at output voxel (2z+a, 2y+b, 2x+c) is a 2x2x2 conv of L
+    // with parity-summed weights: all eight parities together are ONE 3x3x3 conv at LOW resolution with
+    // 8*w output columns (zero weights where a parity does not see a tap) on a replicate-padded L (reflect
+    // padding of the upsampled tensor equals replicate padding of L).  That launch runs with N = 8*w per A
+    // tile instead of 3*w, never materialises the upsampled tensor, and stores its (shift-seeded) result
+    // depth-to-space as 16-bit partial sums, which then seed the accumulators of the w -> w skip conv.
+    const bool use_upconv = d.interp_kind == ANX_INTERP_NEAREST && d.norm_kind != ANX_NORM_INSTANCE &&
+                            !(d.flags & (ANX_FLAG_FORCE_SIMT | ANX_FLAG_NO_UPCONV)) && width[0] == 16 &&
+                            !getenv("ANX_NO_UPCONV");   // the seeded skip conv handles one 16-channel chunk
+    std::vector<std::pair<int, int>> pairs;
     for (int l = nd - 1; l >= 0; --l) {
+        if (use_upconv && l == 0) {
+            e->bufs[cur].shell_rep = 1;
+            mi += 1;                                     // the nn.Upsample slot
+            const int w = width[l], cup = width[l + 1];
+            const bool has_norm = d.norm_kind != ANX_NORM_NONE, has_act = d.act_kind != ANX_ACT_NONE;
+            Logical lg{mi, 3 * w, w, has_norm, (int)e->convs.size(), (int)e->convs.size() + 1};
+            ConvLayer a{};
+            a.module_index = mi; a.cin = cup; a.cout = 8 * w; a.ncols = 8 * w; a.level = l + 1;
+            a.has_norm = false; a.has_act = false; a.is_stem = false; a.is_final = false;
+            a.src_buf = cur; a.dst_buf = -2; a.dst_group_offset = 0; a.d2s_cout = w;
+            a.n_splits = a.ncols > 256 ? a.ncols / 256 : 1;
+            a.ncols_split = a.ncols / a.n_splits;
+            int v = add_buffer(e, l, w);
+            ConvLayer b{};
+            b.module_index = mi; b.cin = w; b.cout = w; b.ncols = (w + 15) / 16 * 16; b.level = l;
+            b.has_norm = has_norm; b.has_act = has_act; b.is_stem = false; b.is_final = false;
+            b.src_buf = cat[l]; b.dst_buf = v; b.dst_group_offset = 0; b.seed_buf = -2;
+            b.n_splits = 1; b.ncols_split = b.ncols;
+            Step sa{}, sb{};
+            sa.kind = sb.kind = STEP_CONV;
+            sa.conv = lg.conv_a; sb.conv = lg.conv_b;
+            snprintf(sa.name, sizeof sa.name, "upconv%d_%dto8x%d_L%d", mi, cup, w, l + 1);
+            snprintf(sb.name, sizeof sb.name, "conv%d_skip%dto%d_L%d", mi, w, w, l);
+            pairs.push_back({lg.conv_a, lg.conv_b});
+            e->logical.push_back(lg);
+            e->convs.push_back(a);
+            e->convs.push_back(b);
+            e->steps.push_back(sa);
+            e->steps.push_back(sb);
+            mi += 1 + (has_norm ? 1 : 0) + (has_act ? 1 : 0);
+            int x = add_buffer(e, l, w);
+            add_conv(e, mi, w, w, l, false, false, v, x, 0);
+            cur = x;
+            continue;
+        }
         Step s{};
         s.kind = STEP_UP;
         s.src_buf = cur;
@@ -261,6 +320,11 @@ void build_program(anx_engine *e) {
         cur = x;
     }
     add_conv(e, mi, g, d.output_nc, 0, true, false, cur, -1, 0);
+    for (auto &pr : pairs) {   // partial-sum buffers go last so the other buffers keep their indices
+        const int P = add_buffer(e, e->convs[pr.second].level, e->convs[pr.second].cout);
+        e->convs[pr.first].dst_buf = P;
+        e->convs[pr.second].seed_buf = P;
+    }
 }
 
 bool shape_ok(const anx_engine *e, int n, int d, int h, int w) {
@@ -327,6 +391,7 @@ ActView view_of(const anx_engine *e, const ShapePlan &p, int buf, int group_offs
     v.D = p.D >> b.level;
     v.H = p.H >> b.level;
     v.W = p.W >> b.level;
+    v.shell_rep = b.shell_rep;
     return v;
 }
 
@@ -391,6 +456,12 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
                        const GatherArgs *ga = nullptr, const ConvGeom *g = nullptr) {
     Epilogue ep{};
     ep.pool_kind = -1;
+    ep.d2s_cout = c.d2s_cout;
+    ep.seed_on = 0;
+    if (c.seed_buf >= 0 && g) {
+        ep.seed_on = 1;
+        ep.seed_src = view_of(e, p, c.seed_buf, 0);
+    }
     if (g && g->fuse_pool) {
         ep.pool_kind = e->desc.pool_kind;
         ep.pool_dst = view_of(e, p, c.pool_dst_buf, 0);
@@ -512,8 +583,12 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                 src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
         } else {
             const int grid = std::min(g.total_tiles, e->num_sms);
-            conv3_umma_kernel<<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
-                                                                          (const uint8_t *)c.d_wpack, ep);
+            if (ep.seed_on)
+                conv3_umma_kernel<true><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
+                                                                                    (const uint8_t *)c.d_wpack, ep);
+            else
+                conv3_umma_kernel<false><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
+                                                                                     (const uint8_t *)c.d_wpack, ep);
         }
         break;
     }
@@ -630,7 +705,9 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
         c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
     }
-    cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+    cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(conv3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (err == cudaSuccess)
@@ -665,12 +742,12 @@ void anx_engine_destroy(anx_engine *e) {
     delete e;
 }
 
-int32_t anx_engine_num_convs(const anx_engine *e) { return e ? (int32_t)e->convs.size() : -1; }
+int32_t anx_engine_num_convs(const anx_engine *e) { return e ? (int32_t)e->logical.size() : -1; }
 
 anx_status anx_engine_conv_info(const anx_engine *e, int32_t k, int32_t *module_index, int32_t *cin, int32_t *cout,
                                 int32_t *has_norm) {
-    if (!e || k < 0 || k >= (int)e->convs.size()) return ANX_ERR_BAD_ARG;
-    const ConvLayer &c = e->convs[k];
+    if (!e || k < 0 || k >= (int)e->logical.size()) return ANX_ERR_BAD_ARG;
+    const Logical &c = e->logical[k];
     if (module_index) *module_index = c.module_index;
     if (cin) *cin = c.cin;
     if (cout) *cout = c.cout;
@@ -678,51 +755,18 @@ anx_status anx_engine_conv_info(const anx_engine *e, int32_t k, int32_t *module_
     return ANX_OK;
 }
 
-anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, const float *bias,
-                               const float *bn_w, const float *bn_b, const float *bn_mean, const float *bn_var,
-                               int32_t location) {
-    if (!e) return ANX_ERR_BAD_ARG;
-    if (k < 0 || k >= (int)e->convs.size() || !weight) return e->fail(ANX_ERR_BAD_ARG, "bad conv ordinal or null weight");
-    ConvLayer &c = e->convs[k];
-    const bool fold_bn = c.has_norm && e->desc.norm_kind == ANX_NORM_BATCH_EVAL;
-    if (fold_bn && (!bn_w || !bn_b || !bn_mean || !bn_var))
-        return e->fail(ANX_ERR_BAD_ARG, "conv %d is followed by BatchNorm: its four arrays are required", c.module_index);
-    ANX_CUDA(e, cudaSetDevice(e->desc.device));
-    const size_t nw = (size_t)c.cout * c.cin * 27;
-    std::vector<float> hw(nw), hb, g1, g2, g3, g4;
-    auto fetch = [&](const float *src, std::vector<float> &dst, size_t n) -> cudaError_t {
-        dst.resize(n);
-        if (location == ANX_LOC_DEVICE) return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost);
-        std::memcpy(dst.data(), src, n * sizeof(float));
-        return cudaSuccess;
-    };
-    ANX_CUDA(e, fetch(weight, hw, nw));
-    if (bias) ANX_CUDA(e, fetch(bias, hb, c.cout));
-    std::vector<float> scale(c.cout, 1.0f), shift(c.ncols, 0.0f);
-    if (fold_bn) {
-        ANX_CUDA(e, fetch(bn_w, g1, c.cout));
-        ANX_CUDA(e, fetch(bn_b, g2, c.cout));
-        ANX_CUDA(e, fetch(bn_mean, g3, c.cout));
-        ANX_CUDA(e, fetch(bn_var, g4, c.cout));
-        // eval BatchNorm folded into the conv: y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
-        for (int o = 0; o < c.cout; ++o) {
-            scale[o] = g1[o] / std::sqrt(g4[o] + e->desc.norm_eps);
-            shift[o] = g2[o] - g3[o] * scale[o] + (bias ? hb[o] * scale[o] : 0.0f);
-        }
-    } else if (bias && !c.inorm) {   // a bias in front of InstanceNorm is cancelled by the mean subtraction
-        for (int o = 0; o < c.cout; ++o) shift[o] = hb[o];
-    }
-
+// Packs and uploads one launch's parameters: `w` = [c.cout][c.cin][27] fp32 with every fold already
+// applied, `shift` = [c.ncols] accumulator seeds.
+static anx_status upload_conv(anx_engine *e, ConvLayer &c, const std::vector<float> &w, const std::vector<float> &shift) {
     if (c.d_wpack) { cudaFree(c.d_wpack); c.d_wpack = nullptr; }
     if (c.d_bias) { cudaFree(c.d_bias); c.d_bias = nullptr; }
     c.ready = false;
     if (c.is_stem) {
-        // fp32 [cin][27][ncols]
+        // fp32 [cin][27][ncols] for the CUDA-core stem
         std::vector<float> pk((size_t)c.cin * 27 * c.ncols, 0.0f);
         for (int o = 0; o < c.cout; ++o)
             for (int i = 0; i < c.cin; ++i)
-                for (int t = 0; t < 27; ++t)
-                    pk[((size_t)i * 27 + t) * c.ncols + o] = hw[((size_t)o * c.cin + i) * 27 + t] * scale[o];
+                for (int t = 0; t < 27; ++t) pk[((size_t)i * 27 + t) * c.ncols + o] = w[((size_t)o * c.cin + i) * 27 + t];
         c.wpack_bytes = pk.size() * sizeof(float);
         ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
         ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
@@ -735,7 +779,7 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
                 for (int i = 0; i < c.cin; ++i)
                     for (int kz = 0; kz < 3; ++kz)
                         for (int t = 0; t < 9; ++t) {
-                            const float v = hw[((size_t)o * c.cin + i) * 27 + kz * 9 + t] * scale[o];
+                            const float v = w[((size_t)o * c.cin + i) * 27 + kz * 9 + t];
                             const uint16_t hi = f32_to_bf16_rne(v);
                             uint32_t hb32 = (uint32_t)hi << 16;
                             float hf;
@@ -765,7 +809,7 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
                     const int grp = c.fold ? 0 : kz;
                     const int row = c.fold ? (2 - kz) * W + ol : ol;
                     for (int t = 0; t < 9; ++t) {
-                        const float v = hw[((size_t)o * c.cin + i) * 27 + kz * 9 + t] * scale[o];
+                        const float v = w[((size_t)o * c.cin + i) * 27 + kz * 9 + t];
                         pk[((size_t)(split * chunks + ch) * c.groups + grp) * slab + ((size_t)(t * 2 + kc) * R + row) * 8 + el] =
                             e->dt == DT_BF16 ? f32_to_bf16_rne(v) : f32_to_f16_rne(v);
                     }
@@ -779,6 +823,80 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
     ANX_CUDA(e, cudaMemcpy(c.d_bias, shift.data(), c.ncols * sizeof(float), cudaMemcpyHostToDevice));
     c.ready = true;
     return ANX_OK;
+}
+
+anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, const float *bias,
+                               const float *bn_w, const float *bn_b, const float *bn_mean, const float *bn_var,
+                               int32_t location) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (k < 0 || k >= (int)e->logical.size() || !weight) return e->fail(ANX_ERR_BAD_ARG, "bad conv ordinal or null weight");
+    const Logical &L = e->logical[k];
+    ConvLayer &ca = e->convs[L.conv_a];
+    const bool fold_bn = L.has_norm && e->desc.norm_kind == ANX_NORM_BATCH_EVAL;
+    const bool inorm = L.has_norm && e->desc.norm_kind == ANX_NORM_INSTANCE;
+    if (fold_bn && (!bn_w || !bn_b || !bn_mean || !bn_var))
+        return e->fail(ANX_ERR_BAD_ARG, "conv %d is followed by BatchNorm: its four arrays are required", L.module_index);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    const size_t nw = (size_t)L.cout * L.cin * 27;
+    std::vector<float> hw(nw), hb, g1, g2, g3, g4;
+    auto fetch = [&](const float *src, std::vector<float> &dst, size_t n) -> cudaError_t {
+        dst.resize(n);
+        if (location == ANX_LOC_DEVICE) return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost);
+        std::memcpy(dst.data(), src, n * sizeof(float));
+        return cudaSuccess;
+    };
+    ANX_CUDA(e, fetch(weight, hw, nw));
+    if (bias) ANX_CUDA(e, fetch(bias, hb, L.cout));
+    const int ncols = (L.cout + 15) / 16 * 16;
+    std::vector<float> scale(L.cout, 1.0f), shift(ncols, 0.0f);
+    if (fold_bn) {
+        ANX_CUDA(e, fetch(bn_w, g1, L.cout));
+        ANX_CUDA(e, fetch(bn_b, g2, L.cout));
+        ANX_CUDA(e, fetch(bn_mean, g3, L.cout));
+        ANX_CUDA(e, fetch(bn_var, g4, L.cout));
+        // eval BatchNorm folded into the conv: y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
+        for (int o = 0; o < L.cout; ++o) {
+            scale[o] = g1[o] / std::sqrt(g4[o] + e->desc.norm_eps);
+            shift[o] = g2[o] - g3[o] * scale[o] + (bias ? hb[o] * scale[o] : 0.0f);
+        }
+    } else if (bias && !inorm) {   // a bias in front of InstanceNorm is cancelled by the mean subtraction
+        for (int o = 0; o < L.cout; ++o) shift[o] = hb[o];
+    }
+    for (int o = 0; o < L.cout; ++o)
+        for (size_t j = 0; j < (size_t)L.cin * 27; ++j) hw[(size_t)o * L.cin * 27 + j] *= scale[o];
+
+    if (L.conv_b < 0) return upload_conv(e, ca, hw, shift);
+
+    // Decoder conv run as two launches (see build_program).  Input channels [0, w) are the skip tensor,
+    // [w, cin) the upsampled one.
+    ConvLayer &cb = e->convs[L.conv_b];
+    const int w = L.cout, cup = L.cin - w;
+    // low-resolution half: column (p*w + co), p = a*4 + b*2 + c; tap (kz,ky,kx) of the high-resolution kernel
+    // lands on low-resolution offset floor((parity + k - 1) / 2) along each axis
+    std::vector<float> wa((size_t)8 * w * cup * 27, 0.0f), sa((size_t)8 * w, 0.0f);
+    auto lowtap = [](int par, int kk) { const int v = par + kk - 1; return (v < 0 ? -1 : v / 2) + 1; };
+    for (int par = 0; par < 8; ++par) {
+        const int pa = (par >> 2) & 1, pb = (par >> 1) & 1, pc = par & 1;
+        for (int co = 0; co < w; ++co) {
+            sa[(size_t)par * w + co] = shift[co];
+            for (int ci = 0; ci < cup; ++ci)
+                for (int kz = 0; kz < 3; ++kz)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int t = (lowtap(pa, kz) * 3 + lowtap(pb, ky)) * 3 + lowtap(pc, kx);
+                            wa[(((size_t)par * w + co) * cup + ci) * 27 + t] +=
+                                hw[((size_t)co * L.cin + w + ci) * 27 + (kz * 3 + ky) * 3 + kx];
+                        }
+        }
+    }
+    anx_status st = upload_conv(e, ca, wa, sa);
+    if (st != ANX_OK) return st;
+    // skip half: the first w input channels; its accumulators are seeded from the partial sums
+    std::vector<float> wb((size_t)w * w * 27), sb(cb.ncols, 0.0f);
+    for (int co = 0; co < w; ++co)
+        for (int ci = 0; ci < w; ++ci)
+            for (int t = 0; t < 27; ++t) wb[((size_t)co * w + ci) * 27 + t] = hw[((size_t)co * L.cin + ci) * 27 + t];
+    return upload_conv(e, cb, wb, sb);
 }
 
 size_t anx_engine_workspace_bytes(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w) {

@@ -69,10 +69,11 @@ __device__ __forceinline__ void warp_stats_add(const float *s, const float *q, d
 // Padded-coordinate targets of interior coordinate v on an axis of size S:
 // always v+1 (k = 0); additionally the shell cell 0 when v == 1 (k = 1) and S+1
 // when v == S-2 (k = 2) (reflect: shell[0] = x[1], shell[S+1] = x[S-2]).  -1 = none.
-__device__ __forceinline__ int mirror_target(int v, int S, int k) {
+// With replicate shells (rep = 1) the sources are x[0] and x[S-1] instead.
+__device__ __forceinline__ int mirror_target(int v, int S, int k, int rep = 0) {
     if (k == 0) return v + 1;
-    if (k == 1) return v == 1 ? 0 : -1;
-    return v == S - 2 ? S + 1 : -1;
+    if (k == 1) return v == (rep ? 0 : 1) ? 0 : -1;
+    return v == (rep ? S - 1 : S - 2) ? S + 1 : -1;
 }
 
 // Shell copies of one 16-byte voxel group whose interior store went to `p`:
@@ -99,7 +100,10 @@ __device__ __forceinline__ void store_mirrors(uint4 *p, const uint4 &q, int dz, 
         }
     }
 }
-__device__ __forceinline__ int mirror_delta(int v, int S) { return v == 1 ? -2 : (v == S - 2 ? 2 : 0); }
+__device__ __forceinline__ int mirror_delta(int v, int S, int rep = 0) {
+    if (rep) return v == 0 ? -1 : (v == S - 1 ? 1 : 0);      // replicate: shell cell next to the border voxel
+    return v == 1 ? -2 : (v == S - 2 ? 2 : 0);
+}
 
 // Stores `ngroups` (1 or 2) packed 8-channel groups of voxel (n,z,y,x) starting at
 // group g0 into a padded planar buffer, including its reflect-shell copies.
@@ -108,7 +112,8 @@ __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, i
     const size_t row = (size_t)(dst.W + 2), plane = row * (dst.H + 2), gstride = plane * (dst.D + 2);
     uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
     if (dst.D >= 4 && dst.H >= 4 && dst.W >= 4) {
-        const int dz = mirror_delta(z, dst.D), dy = mirror_delta(y, dst.H), dx = mirror_delta(x, dst.W);
+        const int dz = mirror_delta(z, dst.D, dst.shell_rep), dy = mirror_delta(y, dst.H, dst.shell_rep),
+                  dx = mirror_delta(x, dst.W, dst.shell_rep);
         *p = q0;
         if (ngroups > 1) p[gstride] = q1;
         if (dz | dy | dx) {
@@ -119,13 +124,13 @@ __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, i
     }
     // tiny tensors (a size-2 or size-3 axis mirrors one voxel to both sides): generic loops
     for (int a = 0; a < 3; ++a) {
-        const int zt = mirror_target(z, dst.D, a);
+        const int zt = mirror_target(z, dst.D, a, dst.shell_rep);
         if (zt < 0) continue;
         for (int b = 0; b < 3; ++b) {
-            const int yt = mirror_target(y, dst.H, b);
+            const int yt = mirror_target(y, dst.H, b, dst.shell_rep);
             if (yt < 0) continue;
             for (int c = 0; c < 3; ++c) {
-                const int xt = mirror_target(x, dst.W, c);
+                const int xt = mirror_target(x, dst.W, c, dst.shell_rep);
                 if (xt < 0) continue;
                 *dst.at(n, g0, zt, yt, xt) = q0;
                 if (ngroups > 1) *dst.at(n, g0 + 1, zt, yt, xt) = q1;

@@ -28,6 +28,7 @@ struct ActView {            // one tensor inside a padded planar buffer
     int groups_total;       // channel groups per sample in the buffer
     int group_offset;       // first group of this tensor
     int D, H, W;            // interior size
+    int shell_rep;          // shell semantics written by the producer: 0 reflect (x[1] / x[S-2]), 1 replicate (x[0] / x[S-1])
     __host__ __device__ __forceinline__ size_t voxel_index(int n, int g, int zp, int yp, int xp) const {
         return ((((size_t)n * groups_total + (group_offset + g)) * (D + 2) + zp) * (H + 2) + yp) * (size_t)(W + 2) + xp;
     }
@@ -65,6 +66,14 @@ struct Epilogue {
     // pooled tensor with its shell.  pool_kind: -1 off, 0 max, 1 mean.
     int pool_kind;
     ActView pool_dst;
+    // Depth-to-space store (low-resolution half of a decoder conv, see engine.cu "upconv"): the conv's
+    // columns are (parity, channel) with d2s_cout channels per parity p = a*4 + b*2 + c, and the 16
+    // channels of a chunk go to voxel (2z+a, 2y+b, 2x+c) of `dst`, a HIGH-resolution partial-sum tensor.
+    int d2s_cout;
+    // Accumulator seeding from a stored tensor instead of the channel shift (the skip half of that conv):
+    // the partial sums written by the depth-to-space launch.
+    int seed_on;
+    ActView seed_src;
 };
 
 // tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),

@@ -255,7 +255,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             et.store = true;
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
-            umma_epilogue_tile<1>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D);
+            umma_epilogue_tile<false>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);

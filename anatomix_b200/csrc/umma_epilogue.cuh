@@ -25,15 +25,44 @@ struct EpiTile {
 __device__ __forceinline__ int plane_lo(int half, int bz) { return half * ((bz + 1) >> 1); }
 __device__ __forceinline__ int plane_hi(int half, int bz) { return half ? bz : ((bz + 1) >> 1); }
 
-template <int BATCH>
+// Seeded accumulators (ncols = 16: two 8-channel groups per plane): the partial sums of the tile that
+// will reuse an accumulator stage are pulled towards L1 while the warp waits for the MMAs, and loaded
+// for real next to the tcgen05.ld of the plane they replace -- no registers are held across the wait.
+__device__ __forceinline__ const uint4 *seed_ptr(const Epilogue &ep, const EpiTile &t, int b, int group) {
+    return ep.seed_src.at(t.n, group, t.z0 + b + 1, t.y + 1, t.x + 1);
+}
+__device__ __forceinline__ bool seed_valid(const EpiTile &t, bool tile_valid, int b, int D) {
+    return tile_valid && t.in_xy && (t.z0 + b) < D;
+}
+__device__ __forceinline__ void prefetch_seeds(const Epilogue &ep, const EpiTile &t, bool tile_valid, int half, int bz,
+                                               int D) {
+    for (int b = plane_lo(half, bz); b < plane_hi(half, bz); ++b)
+        if (seed_valid(t, tile_valid, b, D)) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(seed_ptr(ep, t, b, 0)));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(seed_ptr(ep, t, b, 1)));
+        }
+}
+__device__ __forceinline__ void load_seed16(const Epilogue &ep, const EpiTile &t, bool tile_valid, int b, int D,
+                                            uint4 &q0, uint4 &q1) {
+    q0 = q1 = make_uint4(0u, 0u, 0u, 0u);
+    if (seed_valid(t, tile_valid, b, D)) {
+        q0 = __ldg(seed_ptr(ep, t, b, 0));
+        q1 = __ldg(seed_ptr(ep, t, b, 1));
+    }
+}
+
+// `next` / `next_valid`: the tile that will reuse this accumulator stage (seeded kernels only).
+template <bool SEEDED>
 __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
-                                                   const float *seed, int half, int bz, int ncols, int D) {
+                                                   const float *seed, int half, int bz, int ncols, int D,
+                                                   const EpiTile &next, bool next_valid) {
     const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
     const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
     const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
-    const int mdx = mirror_delta(t.x, Ww), mdy = mirror_delta(t.y, Hh);
+    const int rep = ep.dst.shell_rep;
+    const int mdx = mirror_delta(t.x, Ww, rep), mdy = mirror_delta(t.y, Hh, rep);
     const size_t rowp = (size_t)(Ww + 2);
     uint4 *pbase = nullptr;
     float *fbase = nullptr;
@@ -85,7 +114,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                         p[0] = a0;
                         p[plane] = c0q;
                         if (ngroups > 1) { p[gstride] = a1; p[gstride + plane] = c1q; }
-                        const int mz0 = mirror_delta(z, Dd), mz1 = mirror_delta(z + 1, Dd);
+                        const int mz0 = mirror_delta(z, Dd, rep), mz1 = mirror_delta(z + 1, Dd, rep);
                         if (mdx | mdy | mz0) {
                             store_mirrors(p, a0, mz0, mdy, mdx, rowp, plane);
                             if (ngroups > 1) store_mirrors(p + gstride, a1, mz0, mdy, mdx, rowp, plane);
@@ -117,28 +146,29 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
             }
             continue;
         }
-        for (int b0 = plane_lo(half, bz); b0 < b_end; b0 += BATCH) {
-            uint32_t r[BATCH][16];
+        for (int b = plane_lo(half, bz); b < b_end; ++b) {
+            uint32_t r[1][16];
+            uint4 sq0, sq1;
             __syncwarp();   // tcgen05.ld / st are warp-collective
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k)
-                if (b0 + k < b_end) tmem_ld16_nowait(acc + (b0 + k) * ncols + cb * 16, r[k]);
+            tmem_ld16_nowait(acc + b * ncols + cb * 16, r[0]);
+            if (SEEDED) load_seed16(ep, next, next_valid, b, D, sq0, sq1);   // L1 hit: prefetched before the wait
             tmem_wait_ld();
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k)
-                if (b0 + k < b_end) {
-                    tmem_ld_ready16(r[k]);
-                    tmem_st16(acc + (b0 + k) * ncols + cb * 16, sd);   // re-seed for a later tile
-                }
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k) {
-                const int b = b0 + k;
-                if (b >= b_end) break;
+            tmem_ld_ready16(r[0]);
+            if (SEEDED) {   // re-seed with the stored partial sums of the tile that reuses this stage
+                float sv[16];
+                unpack_x8(sq0, sv, ep.dt);
+                unpack_x8(sq1, sv + 8, ep.dt);
+                tmem_st16(acc + b * ncols + cb * 16, sv);
+            } else {
+                tmem_st16(acc + b * ncols + cb * 16, sd);   // re-seed for a later tile
+            }
+            {
+                constexpr int kk = 0;
                 const int z = t.z0 + b;
                 const bool ok = t.in_xy && z < D && t.store;
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k][i]);
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[kk][i]);
                 if (ep.stats && ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
@@ -150,11 +180,18 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                     const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
                     if (ngroups <= 0) continue;
                     const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
-                    if (big) {
+                    if (ep.d2s_cout) {
+                        // depth-to-space: chunk = 16 channels of one parity; no shell (only the interior is read back)
+                        const int par = c0 / ep.d2s_cout, co0 = c0 - par * ep.d2s_cout;
+                        uint4 *p = ep.dst.at(t.n, co0 >> 3, 2 * z + ((par >> 2) & 1) + 1, 2 * t.y + ((par >> 1) & 1) + 1,
+                                             2 * t.x + (par & 1) + 1);
+                        *p = q0;
+                        p[(size_t)(Dd + 2) * (Hh + 2) * (Ww + 2)] = q1;
+                    } else if (big) {
                         uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
                         *p = q0;
                         if (ngroups > 1) p[gstride] = q1;
-                        const int mdz = mirror_delta(z, Dd);
+                        const int mdz = mirror_delta(z, Dd, rep);
                         if (mdx | mdy | mdz) {   // shell copies: a few predicated stores, no loops
                             store_mirrors(p, q0, mdz, mdy, mdx, rowp, plane);
                             if (ngroups > 1) store_mirrors(p + gstride, q1, mdz, mdy, mdx, rowp, plane);

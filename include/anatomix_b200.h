@@ -78,6 +78,9 @@ typedef struct anx_unet_desc {
  * tensor is [N, C, D+2, H, W] with one extra plane at each end of D (the neighbouring
  * slab's boundary plane, or the caller's reflect copy at a global face). */
 #define ANX_FLAG_DEPTH_HALO_INPUT 8u
+/* Keep the decoder's level-0 conv as one launch over the materialised upsampled tensor instead of
+ * evaluating its upsampled half at low resolution (tests use this to compare code paths). */
+#define ANX_FLAG_NO_UPCONV 16u
 
 /* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
  * device constants; no parameters yet. */

@@ -110,8 +110,35 @@ def conv3d_reflect(x, w, b):
     return F.conv3d(F.pad(x, (1, 1, 1, 1, 1, 1), mode="reflect"), w, b)
 
 
+def _lowtap(par, k):
+    """Low-resolution tap (0..2) hit by high-resolution tap k (0..2) at output parity par:
+    floor((par + k - 1) / 2) + 1."""
+    return (par + k - 1) // 2 + 1
+
+
+def upconv_lowres(low, w_up, shift, rnd):
+    """Engine emulation of conv(nearest_up2(low)) at the decoder's last level: per output parity
+    (a, b, c) a 3x3x3 conv of the replicate-padded LOW-resolution tensor with parity-summed weights
+    (summed in fp32, then rounded to the storage type), shift added, result rounded (it is stored as
+    16-bit partial sums).  Reflect padding of the upsampled tensor == replicate padding of `low`."""
+    n, _, d, h, w = low.shape
+    co = w_up.shape[0]
+    lp = F.pad(low, (1, 1, 1, 1, 1, 1), mode="replicate")
+    out = torch.empty(n, co, 2 * d, 2 * h, 2 * w)
+    for a in range(2):
+        for b in range(2):
+            for c in range(2):
+                wp = torch.zeros_like(w_up)
+                for kz in range(3):
+                    for ky in range(3):
+                        for kx in range(3):
+                            wp[:, :, _lowtap(a, kz), _lowtap(b, ky), _lowtap(c, kx)] += w_up[:, :, kz, ky, kx]
+                out[:, :, a::2, b::2, c::2] = F.conv3d(lp, rnd(wp)) + shift.view(1, -1, 1, 1, 1)
+    return rnd(out)
+
+
 @torch.no_grad()
-def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False):
+def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False, emulate_upconv=True):
     """Forward of ``Unet(**cfg)`` holding ``state`` (a state dict) on input ``x``
     ``[N, input_nc, D, H, W]`` fp32.  Returns the output, or ``(output, taps)``
     when ``layers`` (module indices) is non-empty (network.py:475-529)."""
@@ -128,6 +155,10 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
     feat, skips, taps = x.to(torch.float32), [], []
     eps = c["norm_eps"]
     n_conv = 0
+    # the engine runs the conv behind the LAST nearest upsample as low-resolution + skip halves
+    split_last = (engine_rounding and emulate_upconv and not training and c["interp"] == "nearest"
+                  and c["norm"] != "instance" and c["ngf"] == 16)
+    pending_low = None
     for pos, (op, idx, ci, co) in enumerate(prog):
         if op == "conv":
             w = g(f"model.{idx}.weight")
@@ -139,6 +170,18 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
                     s = g(f"model.{idx+1}.weight") / torch.sqrt(g(f"model.{idx+1}.running_var") + eps)
                     w = w * s.view(-1, 1, 1, 1, 1)
                     b = g(f"model.{idx+1}.bias") - g(f"model.{idx+1}.running_mean") * s
+                if pending_low is not None:
+                    cs = feat.shape[1] - pending_low.shape[1]          # skip channels come first
+                    zero = torch.zeros(w.shape[0]) if b is None else b
+                    part = upconv_lowres(pending_low, w[:, cs:], zero, _rnd)
+                    feat = conv3d_reflect(feat[:, :cs], _rnd(w[:, :cs]), None) + part
+                    pending_low = None
+                    n_conv += 1
+                    if c["use_skip_connection"] and idx in enc_idx:
+                        skips.append(feat)
+                    if idx in layers:
+                        taps.append(feat.clone())
+                    continue
                 if n_conv > 0:                       # stem conv stays fp32
                     w = _rnd(w)
                 if nxt == "norm" and c["norm"] == "instance":
@@ -177,6 +220,8 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
             if engine_rounding:
                 feat = _rnd(feat)
         elif op == "up":                             # network.py:407
+            if split_last and idx == dec_idx[-1]:
+                pending_low = feat
             if c["interp"] == "nearest":
                 feat = F.interpolate(feat, scale_factor=2, mode="nearest")
             else:

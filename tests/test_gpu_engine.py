@@ -41,14 +41,14 @@ def make_engine(cfg, state, flags=0):
     return eng
 
 
-def check_against_oracle(cfg, state, x, y_gpu, tight=True):
+def check_against_oracle(cfg, state, x, y_gpu, tight=True, upconv=True):
     want = O.unet_forward(cfg, state, x)
     got = y_gpu.float().cpu()
     assert torch.isfinite(got).all()
     r, c = rel_l2(got, want), min_cosine(got, want)
     assert r <= LOOSE_REL and c >= LOOSE_COS, f"loose gate: rel-L2 {r:.3e}, min cosine {c:.5f}"
     if tight:
-        emu = O.unet_forward(cfg, state, x, engine_rounding=True)
+        emu = O.unet_forward(cfg, state, x, engine_rounding=True, emulate_upconv=upconv)
         rt = rel_l2(got, emu)
         assert rt <= TIGHT_REL, f"tight gate: rel-L2 {rt:.3e} vs bf16-emulating oracle"
     return r, c
@@ -110,14 +110,19 @@ def test_tensor_core_path_matches_simt_and_oracle_small(shape, cfgkw):
     state = O.random_state(cfg, seed=5)
     x = rand_input(shape, 9)
     ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
-    eng = make_engine(cfg, state)
+    eng = make_engine(cfg, state, flags=_lib.FLAG_NO_UPCONV)     # same launch structure as the CUDA-core path
     xs = x.cuda()
     y_ref = ref_eng.forward(xs)
     y = eng.forward(xs)
     torch.cuda.synchronize()
     r = rel_l2(y.cpu(), y_ref.cpu())
     assert r < 5e-3, f"tensor-core vs CUDA-core conv: rel-L2 {r:.3e}\n" + localize(eng, ref_eng, shape)
-    check_against_oracle(cfg, state, x, y)
+    check_against_oracle(cfg, state, x, y, upconv=False)
+    # default engine: the decoder's level-0 conv runs as low-resolution + skip launches
+    y_up = make_engine(cfg, state).forward(xs)
+    torch.cuda.synchronize()
+    check_against_oracle(cfg, state, x, y_up)
+    assert rel_l2(y_up.cpu(), y.cpu()) < 1e-2
     # the first layers have had no chance to spread a rounding flip yet
     from gpu_debug import compare
     full = dict(O.DEFAULTS); full.update(cfg)
