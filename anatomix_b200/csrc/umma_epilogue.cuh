@@ -146,12 +146,17 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
             }
             continue;
         }
+        uint4 nq0, nq1;   // seeds of the NEXT plane, loaded one plane ahead (L2 latency hides behind a plane of work)
+        if (SEEDED) load_seed16(ep, next, next_valid, plane_lo(half, bz), D, nq0, nq1);
         for (int b = plane_lo(half, bz); b < b_end; ++b) {
             uint32_t r[1][16];
             uint4 sq0, sq1;
             __syncwarp();   // tcgen05.ld / st are warp-collective
             tmem_ld16_nowait(acc + b * ncols + cb * 16, r[0]);
-            if (SEEDED) load_seed16(ep, next, next_valid, b, D, sq0, sq1);   // L1 hit: prefetched before the wait
+            if (SEEDED) {
+                sq0 = nq0; sq1 = nq1;
+                if (b + 1 < b_end) load_seed16(ep, next, next_valid, b + 1, D, nq0, nq1);
+            }
             tmem_wait_ld();
             tmem_ld_ready16(r[0]);
             if (SEEDED) {   // re-seed with the stored partial sums of the tile that reuses this stage
