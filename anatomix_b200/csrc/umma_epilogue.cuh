@@ -4,9 +4,7 @@
 // or fp32 NCDHW / fused all-gather stores for the network output; and the re-seeding
 // of the drained accumulator columns with the per-channel shift.
 //
-// One call handles the planes b = half, half+2, ... of this warp's TMEM lane quadrant.
-// BATCH tcgen05.ld are issued back to back before the single wait, so the TMEM read
-// latency is paid once per batch instead of once per plane.
+// One call handles the planes [plane_lo, plane_hi) of this warp's TMEM lane quadrant.
 #pragma once
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -168,12 +166,11 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                 tmem_st16(acc + b * ncols + cb * 16, sd);   // re-seed for a later tile
             }
             {
-                constexpr int kk = 0;
                 const int z = t.z0 + b;
                 const bool ok = t.in_xy && z < D && t.store;
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[kk][i]);
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[0][i]);
                 if (ep.stats && ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }

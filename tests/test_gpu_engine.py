@@ -284,6 +284,42 @@ def test_module_routes_to_engine_and_back(state_6m):
     assert list(m._anx_binding.engines) == [torch.device("cuda", 0)]
 
 
+@pytest.mark.parametrize("input_nc", [2, 3, 4])
+def test_multichannel_stem(input_nc):
+    """Stem with several input channels (K = 9*Cin taps spread over 2-3 tensor-core K chunks)."""
+    cfg = small_cfg(input_nc=input_nc, num_downs=1)
+    state = O.random_state(cfg, seed=30 + input_nc)
+    x = rand_input((2, input_nc, 8, 16, 16), 31)
+    eng = make_engine(cfg, state)
+    check_against_oracle(cfg, state, x, eng.forward(x.cuda()))
+
+
+def test_storage_type_override(state_6m):
+    """ANX_FLAG_STORE_FP16 on a BatchNorm network: 8x smaller rounding error than bf16
+    (inputs in [0,1] keep the activations far inside fp16 range)."""
+    from anatomix_b200 import _lib
+    x = rand_input((1, 1, 32, 32, 32), 0)
+    want = O.unet_forward(CFG_6M, state_6m, x)
+    y16 = make_engine(CFG_6M, state_6m, flags=_lib.FLAG_STORE_FP16).forward(x.cuda()).cpu()
+    ybf = make_engine(CFG_6M, state_6m).forward(x.cuda()).cpu()
+    r16, rbf = rel_l2(y16, want), rel_l2(ybf, want)
+    assert r16 < 4e-3 and r16 < 0.4 * rbf, (r16, rbf)
+
+
+def test_sliding_window_on_engine(state_6m):
+    """Whole-scan extraction: engine as the window predictor vs the
+    oracle as the predictor, same window grid and gaussian blend."""
+    from anatomix_b200.sliding import sliding_window_features
+    x = rand_input((1, 1, 48, 32, 64), 8)
+    eng = make_engine(CFG_6M, state_6m)
+    got = sliding_window_features(x.cuda(), (32, 32, 32), 6, eng.forward, overlap=0.5, mode="gaussian",
+                                  sigma_scale=0.25).cpu()
+    want = sliding_window_features(x, (32, 32, 32), 6, lambda t: O.unet_forward(CFG_6M, state_6m, t), overlap=0.5,
+                                   mode="gaussian", sigma_scale=0.25)
+    assert got.shape == (1, 16, 48, 32, 64)
+    assert rel_l2(got, want) <= LOOSE_REL and min_cosine(got, want) >= LOOSE_COS
+
+
 def test_host_buffer_entry_point(state_6m):
     """anx_engine_forward_host: pinned host buffers in and out, chunked upload / compute /
     download pipeline; must equal the device-buffer forward bit for bit."""
