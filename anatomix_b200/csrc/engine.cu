@@ -537,6 +537,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             g.b_bytes = (uint32_t)(g.kq * 2 * 3 * g.ncols * 16);
             g.smem_bytes = 2 * ((g.brick_bytes + 127) & ~127u) + STEM_A_SLOTS * 2 * g.a_tile_bytes + 2 * g.b_bytes +
                            (uint32_t)sizeof(StemShared);
+            if (g.smem_bytes > (uint32_t)e->max_smem)
+                return e->fail(ANX_ERR_UNSUPPORTED, "stem tile does not fit shared memory (%u bytes)", g.smem_bytes);
             CUtensorMap tm;
             cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)(p.D + 2 * zh0), (cuuint64_t)p.N * c.cin};
             cuuint64_t strides[3] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4,
@@ -711,11 +713,11 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        err = cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        err = cudaFuncSetAttribute(stem_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        err = cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err != cudaSuccess) {
         delete e;
         return ANX_ERR_CUDA;
