@@ -58,41 +58,69 @@ def weights():
     return random_state(CFG_6M, 0), "seeded random weights"
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes (read + write) of the conv kernel's launches in one 8x128^3 forward, from the committed
+    ncu --set full capture (profiles/r1_traffic.json); None when that file is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("conv3_umma_kernel_dram_bytes_per_step")
+
+
 def synth(n, seed):
     return torch.rand(n, 1, VOL, VOL, VOL, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML every few
+    milliseconds (falls back to polling nvidia-smi when pynvml is unavailable)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.sm, self.bits, self.max_mhz, self.stop_flag = index, [], 0, None, threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES remapping via the UUID of the torch device
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    handle = h
+            self.handle = handle or pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml:
+                    self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    self.bits |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.stop_flag.wait(0.004)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index),
+                                          "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    self.stop_flag.wait(0.2)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [name for bit, name in self.REASONS.items() if self.bits & bit]
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_port_time(steps, warmup, state):
@@ -212,7 +240,7 @@ def main():
                 acc[name] = 0.0
                 order.append(name)
             acc[name] += t / reps
-    conv_ms = sum(t for n, t in acc.items() if n.startswith("conv") and not n.startswith("conv0_"))
+    conv_ms = sum(t for n, t in acc.items() if "conv" in n and not n.startswith("conv0_"))   # conv3_umma_kernel launches
     fwd_ms = sum(acc.values())
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -302,10 +330,11 @@ def main():
                     "h2d_bytes_per_step": B * VOL ** 3 * 4, "d2h_bytes_per_step": B * 16 * VOL ** 3 * 4},
             "gpu_launches": eng.launches_per_forward(B, VOL, VOL, VOL) * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv3_umma_kernel (19 launches per forward)",
+            "roofline": {"bound": "tensor", "kernel": "conv3_umma_kernel (%d launches per forward)" % sum(
+                             1 for n in order if "conv" in n and not n.startswith("conv0_")),
                          "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained)",
-                         "traffic": None,
+                         "traffic": ncu_traffic_bytes(),
                          "whole_forward": {"ms_sum_of_launches": fwd_ms,
                                            "hbm_gbs_algorithmic": ALGO_MB_PER_VOL * 1e6 * B / (fwd_ms / 1e3) / 1e9,
                                            "hbm_peak": peaks["hbm"],
