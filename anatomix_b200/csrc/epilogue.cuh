@@ -44,6 +44,16 @@ __device__ __forceinline__ void unpack_x8(const uint4 &q, float *v, int dt) {
     }
 }
 
+// element-wise max of two packed 16-bit pairs of the storage type
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b, int dt) {
+    if (dt == DT_BF16) {
+        __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&a), *reinterpret_cast<__nv_bfloat162 *>(&b));
+        return *reinterpret_cast<uint32_t *>(&r);
+    }
+    __half2 r = __hmax2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
 // Warp-level instance-norm statistics: every lane brings 16 per-channel partial sums
 // `s` and 16 partial sums of squares `q` (its own voxels).  A butterfly
 // reduce-scatter (31 shuffles for the 32 values) leaves lane l with the warp total of

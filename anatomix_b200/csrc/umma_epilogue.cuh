@@ -126,7 +126,22 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                         store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z + 1, t.y, t.x, c0q, c1q);
                     }
                 }
-                // pool the STORED (rounded) values, as the reference pools the stored activation
+                if (ep.pool_kind == 0) {
+                    // max pooling on the packed 16-bit pairs: 16 shuffles + 24 two-wide max, no unpack / repack
+                    uint32_t pk[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const uint32_t pc[8] = {c0q.x, c0q.y, c0q.z, c0q.w, c1q.x, c1q.y, c1q.z, c1q.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pk[i] = max16x2(pk[i], pc[i], ep.dt);
+                        pk[i] = max16x2(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1), ep.dt);
+                        pk[i] = max16x2(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 8), ep.dt);
+                    }
+                    if (ok && ngroups > 0 && !((t.x | t.y) & 1))
+                        store_padded_groups(ep.pool_dst, t.n, c0 >> 3, ngroups, z >> 1, t.y >> 1, t.x >> 1,
+                                            make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                    continue;
+                }
+                // mean pooling of the STORED (rounded) values, as the reference pools the stored activation
                 unpack_x8(a0, v0, ep.dt); unpack_x8(a1, v0 + 8, ep.dt);
                 unpack_x8(c0q, v1, ep.dt); unpack_x8(c1q, v1 + 8, ep.dt);
 #pragma unroll
@@ -145,7 +160,23 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
             continue;
         }
         uint4 nq0, nq1;   // seeds of the NEXT plane, loaded one plane ahead (L2 latency hides behind a plane of work)
-        if (SEEDED) load_seed16(ep, next, next_valid, plane_lo(half, bz), D, nq0, nq1);
+        const uint4 *sbase = nullptr;          // seed tensor at (next tile, plane 0, this voxel), group 0
+        size_t splane = 0, sgroup = 0;
+        bool s_xy = false;
+        auto seed_load = [&](int b, uint4 &q0, uint4 &q1) {
+            q0 = q1 = make_uint4(0u, 0u, 0u, 0u);
+            if (s_xy && (next.z0 + b) < D) {
+                q0 = __ldg(sbase + (size_t)b * splane);
+                q1 = __ldg(sbase + (size_t)b * splane + sgroup);
+            }
+        };
+        if (SEEDED) {
+            s_xy = next_valid && next.in_xy;
+            splane = (size_t)(ep.seed_src.H + 2) * (ep.seed_src.W + 2);
+            sgroup = splane * (ep.seed_src.D + 2);
+            sbase = seed_ptr(ep, next, 0, 0);
+            seed_load(plane_lo(half, bz), nq0, nq1);
+        }
         for (int b = plane_lo(half, bz); b < b_end; ++b) {
             uint32_t r[1][16];
             uint4 sq0, sq1;
@@ -153,7 +184,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
             tmem_ld16_nowait(acc + b * ncols + cb * 16, r[0]);
             if (SEEDED) {
                 sq0 = nq0; sq1 = nq1;
-                if (b + 1 < b_end) load_seed16(ep, next, next_valid, b + 1, D, nq0, nq1);
+                if (b + 1 < b_end) seed_load(b + 1, nq0, nq1);
             }
             tmem_wait_ld();
             tmem_ld_ready16(r[0]);
