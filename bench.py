@@ -178,8 +178,7 @@ def main():
         return
 
     import torch.distributed as dist
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the ONE JSON line
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

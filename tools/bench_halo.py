@@ -17,8 +17,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
