@@ -232,6 +232,8 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
         return "input is not a CUDA tensor"
     if len(layers) > 0:
         return "feature taps requested"
+    if x.numel() == 0:
+        return "empty batch"
     if cfg["dimension"] != 3 or x.dim() != 5:
         return "not a 3-D network / 5-D input"
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):

@@ -336,6 +336,51 @@ def test_host_buffer_entry_point(state_6m):
         assert torch.equal(yh, want), f"host-buffer forward differs at batch {n}"
 
 
+def test_engine_reuse_across_shapes_and_streams(state_6m):
+    """One engine, several shapes back to back (plan cache), and two CUDA streams with their own
+    workspaces running concurrently (the engine is immutable after packing)."""
+    import ctypes as C
+    eng = make_engine(CFG_6M, state_6m)
+    shapes = [(1, 1, 32, 32, 32), (2, 1, 32, 48, 32), (1, 1, 64, 32, 32), (1, 1, 32, 32, 32), (3, 1, 32, 32, 64)]
+    outs = []
+    for i, sh in enumerate(shapes):
+        x = rand_input(sh, 40 + i)
+        outs.append((x, eng.forward(x.cuda())))
+    torch.cuda.synchronize()
+    for x, y in outs:
+        assert rel_l2(y.cpu(), O.unet_forward(CFG_6M, state_6m, x)) <= LOOSE_REL
+    # two streams, distinct workspaces and outputs
+    xa, xb = rand_input((1, 1, 32, 32, 32), 50).cuda(), rand_input((1, 1, 32, 32, 32), 51).cuda()
+    want_a, want_b = eng.forward(xa).clone(), eng.forward(xb).clone()
+    need = eng.workspace_bytes(1, 32, 32, 32)
+    ws = [torch.empty(need, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ys = [torch.empty_like(want_a) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k, (s, x) in enumerate(zip(streams, (xa, xb))):
+            st = eng.lib.anx_engine_forward(eng._h, x.data_ptr(), ys[k].data_ptr(), 1, 32, 32, 32, ws[k].data_ptr(), need,
+                                            s.cuda_stream)
+            assert st == 0
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], want_a) and torch.equal(ys[1], want_b)
+
+
+def test_empty_batch_and_cpu_inputs_stay_on_torch(state_6m):
+    from anatomix_b200 import Unet
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(torch.zeros(0, 1, 32, 32, 32, device="cuda")) == "empty batch"
+        assert m(torch.zeros(0, 1, 32, 32, 32, device="cuda")).shape == (0, 16, 32, 32, 32)
+        assert "autocast" in m.engine_ineligible_reason(torch.zeros(1, 1, 32, 32, 32, device="cuda")) \
+            if torch.is_autocast_enabled() else True
+        assert m.engine_ineligible_reason(torch.zeros(1, 1, 32, 32, 32, device="cuda", dtype=torch.float64)) == \
+            "input is not fp32"
+
+
 def test_errors_mirror_the_reference(state_6m):
     from anatomix_b200.engine import Engine, EngineError
     eng = make_engine(CFG_6M, state_6m)
