@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) {
 
 // SEEDED: accumulators start from a stored partial-sum tensor (ep.seed_src) instead of the channel
 // shift -- the skip half of a decoder conv whose upsampled half was evaluated at low resolution.
-template <bool SEEDED>
+template <int MODE>   // EpiMode: the epilogue variant compiled into this instantiation
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g, const uint8_t *__restrict__ wpack,
                   const Epilogue ep) {
@@ -80,6 +80,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
     uint8_t *b_ring = a_ring + (size_t)g.a_stages * g.a_stage_bytes;
     UmmaShared *sh = reinterpret_cast<UmmaShared *>(b_ring + (size_t)g.b_stages * g.b_stage_bytes);
 
+    constexpr bool SEEDED = MODE == EPI_SEEDED;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int acc_cols = g.bz * g.ncols;   // TMEM columns per accumulator stage
@@ -252,7 +253,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
             if (SEEDED) prefetch_seeds(ep, en, next_valid, half, g.bz, g.D);   // in flight during the wait
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
             tc_fence_after();
-            umma_epilogue_tile<SEEDED>(ep, et, lane_base + s * acc_cols, sh->shift + (next % g.n_splits) * g.ncols, half,
+            umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift + (next % g.n_splits) * g.ncols, half,
                                        g.bz, g.ncols, g.D, en, next_valid);
             tmem_wait_st();
             tc_fence_before();

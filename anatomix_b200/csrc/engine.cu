@@ -550,12 +550,14 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return e->fail(ANX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the stem input", (int)r);
             const int grid = std::min(g.total_tiles, e->num_sms);
-            if (g.kq == 1)
-                stem_umma_kernel<1><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
-            else if (g.kq == 2)
-                stem_umma_kernel<2><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
-            else
-                stem_umma_kernel<3><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, (const uint8_t *)c.d_wstem, ep);
+            const uint8_t *ws_ = (const uint8_t *)c.d_wstem;
+#define ANX_STEM(KQ_, MODE_) stem_umma_kernel<KQ_, MODE_><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, ws_, ep)
+            if (ep.stats) {
+                if (g.kq == 1) ANX_STEM(1, EPI_STATS); else if (g.kq == 2) ANX_STEM(2, EPI_STATS); else ANX_STEM(3, EPI_STATS);
+            } else {
+                if (g.kq == 1) ANX_STEM(1, EPI_PADDED); else if (g.kq == 2) ANX_STEM(2, EPI_PADDED); else ANX_STEM(3, EPI_PADDED);
+            }
+#undef ANX_STEM
             break;
         }
         const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
@@ -585,12 +587,15 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                 src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
         } else {
             const int grid = std::min(g.total_tiles, e->num_sms);
-            if (ep.seed_on)
-                conv3_umma_kernel<true><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
-                                                                                    (const uint8_t *)c.d_wpack, ep);
-            else
-                conv3_umma_kernel<false><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g,
-                                                                                     (const uint8_t *)c.d_wpack, ep);
+            const uint8_t *wp_ = (const uint8_t *)c.d_wpack;
+#define ANX_CONV(MODE_) conv3_umma_kernel<MODE_><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g, wp_, ep)
+            if (ep.mode == OUT_NCDHW_F32) { if (ep.n_peers > 0) ANX_CONV(EPI_F32_PEERS); else ANX_CONV(EPI_F32); }
+            else if (ep.seed_on) ANX_CONV(EPI_SEEDED);
+            else if (ep.stats) ANX_CONV(EPI_STATS);
+            else if (ep.d2s_cout) ANX_CONV(EPI_D2S);
+            else if (ep.pool_kind >= 0) ANX_CONV(EPI_POOL);
+            else ANX_CONV(EPI_PADDED);
+#undef ANX_CONV
         }
         break;
     }
@@ -707,17 +712,16 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
         c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
     }
-    cudaError_t err = cudaFuncSetAttribute(conv3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(conv3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+    cudaError_t err = cudaSuccess;
+#define ANX_SMEM(K_) if (err == cudaSuccess) err = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem)
+    ANX_SMEM(conv3_umma_kernel<EPI_PADDED>); ANX_SMEM(conv3_umma_kernel<EPI_POOL>); ANX_SMEM(conv3_umma_kernel<EPI_D2S>);
+    ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
+    ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>);
+    ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
+    ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
+#undef ANX_SMEM
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
     if (err != cudaSuccess) {
         delete e;
         return ANX_ERR_CUDA;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void split_hi_lo(float x0, float x1, uint32_t &hi, ui
     lo = pack_bf16x2(x0 - h0, x1 - h1);
 }
 
-template <int KQ>   // K chunks of 16: 1 for Cin = 1, 2 for Cin = 2..3, 3 for Cin = 4
+template <int KQ, int MODE>   // K chunks of 16 (1 for Cin = 1, 2 for Cin = 2..3, 3 for Cin = 4); EpiMode
 __global__ void __launch_bounds__(STEM_THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, const uint8_t *__restrict__ wpack,
                  const Epilogue ep) {
@@ -255,7 +255,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             et.store = true;
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
-            umma_epilogue_tile<false>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);
+            umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);

@@ -49,8 +49,19 @@ __device__ __forceinline__ void load_seed16(const Epilogue &ep, const EpiTile &t
     }
 }
 
+// Compile-time epilogue variants: each launch carries only the code of its own path.
+enum EpiMode : int {
+    EPI_PADDED = 0,      // 16-bit padded planar store (+ shell)
+    EPI_POOL = 1,        // ... and the fused 2x2x2 pooled tensor
+    EPI_D2S = 2,         // depth-to-space partial sums (low-resolution half of a decoder conv)
+    EPI_STATS = 3,       // ... raw output + instance-norm sums
+    EPI_F32 = 4,         // fp32 NCDHW network output
+    EPI_F32_PEERS = 5,   // ... into every peer's gather buffer
+    EPI_SEEDED = 6       // padded store, accumulators re-seeded from stored partial sums
+};
+
 // `next` / `next_valid`: the tile that will reuse this accumulator stage (seeded kernels only).
-template <bool SEEDED>
+template <int MODE>
 __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
                                                    const float *seed, int half, int bz, int ncols, int D,
                                                    const EpiTile &next, bool next_valid) {
@@ -58,13 +69,15 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
+    constexpr bool SEEDED = MODE == EPI_SEEDED;
+    constexpr bool PADDED = MODE != EPI_F32 && MODE != EPI_F32_PEERS;
     const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
     const int rep = ep.dst.shell_rep;
     const int mdx = mirror_delta(t.x, Ww, rep), mdy = mirror_delta(t.y, Hh, rep);
     const size_t rowp = (size_t)(Ww + 2);
     uint4 *pbase = nullptr;
     float *fbase = nullptr;
-    if (ep.mode == OUT_PADDED_BF16)
+    if constexpr (PADDED)
         pbase = ep.dst.at(t.n, t.chan0 >> 3, t.z0 + 1, t.y + 1, t.x + 1);
     else
         fbase = ep.out_f32 + ((size_t)t.n * ep.cout + t.chan0) * vol + ((size_t)t.z0 * Hh + t.y) * Ww + t.x;
@@ -78,12 +91,12 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
             sd[4 * i] = f.x; sd[4 * i + 1] = f.y; sd[4 * i + 2] = f.z; sd[4 * i + 3] = f.w;
         }
         float s16[16], q16[16];
-        if (ep.stats) {
+        if constexpr (MODE == EPI_STATS) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s16[i] = 0.0f; q16[i] = 0.0f; }
         }
         const int b_end = plane_hi(half, bz);
-        if (ep.pool_kind >= 0) {
+        if constexpr (MODE == EPI_POOL) {
             // ---- fused 2x2x2 pooling: planes in pairs (b, b+1); requires an even, pair-aligned plane range
             const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
             for (int b = plane_lo(half, bz); b < b_end; b += 2) {
@@ -202,18 +215,20 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[0][i]);
-                if (ep.stats && ok) {
+                if constexpr (MODE == EPI_STATS) {
+                    if (ok) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
+                        for (int i = 0; i < 16; ++i) { s16[i] += v[i]; q16[i] = fmaf(v[i], v[i], q16[i]); }
+                    }
                 }
                 if (!ok) continue;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = activate(v[i], ep.act, ep.slope);
-                if (ep.mode == OUT_PADDED_BF16) {
+                if constexpr (PADDED) {
                     const int ngroups = (ep.cout - c0) >= 16 ? 2 : ((ep.cout - c0 + 7) >> 3);
                     if (ngroups <= 0) continue;
                     const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
-                    if (ep.d2s_cout) {
+                    if constexpr (MODE == EPI_D2S) {
                         // depth-to-space: chunk = 16 channels of one parity; no shell (only the interior is read back)
                         const int par = c0 / ep.d2s_cout, co0 = c0 - par * ep.d2s_cout;
                         uint4 *p = ep.dst.at(t.n, co0 >> 3, 2 * z + ((par >> 2) & 1) + 1, 2 * t.y + ((par >> 1) & 1) + 1,
@@ -232,7 +247,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                     } else {
                         store_padded_groups(ep.dst, t.n, c0 >> 3, ngroups, z, t.y, t.x, q0, q1);
                     }
-                } else if (ep.n_peers == 0) {
+                } else if constexpr (MODE == EPI_F32) {
                     float *o = fbase + (size_t)(cb * 16) * vol + (size_t)b * Hh * Ww;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -250,7 +265,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                 }
             }
         }
-        if (ep.stats) {   // whole warp converged: the loops above have warp-uniform trip counts
+        if constexpr (MODE == EPI_STATS) {   // whole warp converged: the loops above have warp-uniform trip counts
             __syncwarp();
             warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2);
         }
