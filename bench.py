@@ -178,7 +178,11 @@ def main():
         return
 
     import torch.distributed as dist
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the ONE JSON line
+    # Library chatter (NCCL prints its version banner on fd 1) must not share stdout with the ONE JSON
+    # line: everything written to fd 1 from here on goes to stderr; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -349,7 +353,7 @@ def main():
                                     "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "4 single-volume 128^3 forwards (1 warm-up) of the oracle's "
                                               "torch-ATen port of the reference CPU path"}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
