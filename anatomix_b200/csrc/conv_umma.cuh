@@ -106,6 +106,14 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             uint32_t ka = 0, kb = 0;
+            if (g.b_static && blockIdx.x < g.total_tiles) {   // the one weight slab of this layer: resident for the whole launch
+                if (g.ablate & 8) {
+                    mbar_arrive(&sh->full_b[0]);
+                } else {
+                    mbar_arrive_expect_tx(&sh->full_b[0], g.b_stage_bytes);
+                    bulk_load_1d(b_ring, wpack, g.b_stage_bytes, &sh->full_b[0]);
+                }
+            }
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(g, tile);
                 for (int c = 0; c < g.cin_chunks; ++c) {
@@ -119,6 +127,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                                     t.y0, t.z0, t.n * g.in_groups_total + g.in_group_offset + 2 * c);
                     }
                     ++ka;
+                    if (g.b_static) continue;
                     for (int grp = 0; grp < g.groups; ++grp) {
                         const uint32_t sb = kb % g.b_stages;
                         mbar_wait(&sh->empty_b[sb], ((kb / g.b_stages) & 1) ^ 1, 2);
@@ -157,8 +166,9 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                 mbar_wait_warp(&sh->full_a[sa], (ka / g.a_stages) & 1, 4);
                 const uint32_t a_lo = ((smem_u32(a_ring + (size_t)sa * g.a_stage_bytes) & 0x3FFFF) >> 4) | a_lbo_bits;
                 for (int grp = 0; grp < g.groups; ++grp) {
-                    const uint32_t sb = kb % g.b_stages;
-                    mbar_wait_warp(&sh->full_b[sb], (kb / g.b_stages) & 1, 5);
+                    const uint32_t sb = g.b_static ? 0u : kb % g.b_stages;
+                    // a static slab completes phase 0 once and is never recycled: parity 0 stays satisfied
+                    mbar_wait_warp(&sh->full_b[sb], g.b_static ? 0u : (kb / g.b_stages) & 1, 5);
                     tc_fence_after();
                     const uint32_t b_lo = ((smem_u32(b_ring + (size_t)sb * g.b_stage_bytes) & 0x3FFFF) >> 4) | b_lbo_bits;
                     if (g.ablate & 1) {
@@ -192,7 +202,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                                                make_desc(b_hi, b_lo + t * b_tap), idesc);
                         }
                     }
-                    umma_commit_warp(&sh->empty_b[sb]);
+                    if (!g.b_static) umma_commit_warp(&sh->empty_b[sb]);
                     ++kb;
                 }
                 umma_commit_warp(&sh->empty_a[sa]);

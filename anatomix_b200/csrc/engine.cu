@@ -350,8 +350,13 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.cin_chunks = c.cin / 16;
     g.in_groups_total = in_groups_total;
     g.in_group_offset = 0;
-    // output planes per tile: as many as TMEM double buffering allows, at most 8
+    // Single-slab layers (one 16-channel chunk, folded dz, no channel split: the 16 -> 16 convs) use the
+    // same B image for every tile: it is loaded once per CTA and stays in shared memory.
+    g.b_static = (c.fold && g.cin_chunks == 1 && c.n_splits == 1 && !getenv("ANX_NO_BSTATIC")) ? 1 : 0;
+    // output planes per tile: as many as TMEM double buffering allows, at most 8 -- or 16 for the thin
+    // single-slab layers, whose MMA count per output plane is 9 * (bz + 2) / bz (all of TMEM, two A stages)
     int bz = std::max(1, std::min(8, 256 / g.ncols));
+    if (g.b_static && g.ncols == 16 && D >= 16 && !getenv("ANX_NO_BZ16")) bz = 16;
     g.acc_stages = 2;
     bz = std::min(bz, D);
     g.bz = bz;
@@ -372,10 +377,12 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     const size_t budget = (size_t)e->max_smem - sizeof(UmmaShared) - 1024;
     g.a_stages = 3;
     g.b_stages = 2;
-    while (g.a_stages > 1 && (size_t)g.a_stages * g.a_stage_bytes + 2u * g.b_stage_bytes > budget) --g.a_stages;
+    const size_t b_reserve = (g.b_static ? 1u : 2u) * (size_t)g.b_stage_bytes;
+    while (g.a_stages > 1 && (size_t)g.a_stages * g.a_stage_bytes + b_reserve > budget) --g.a_stages;
     size_t left = budget - (size_t)g.a_stages * g.a_stage_bytes;
     g.b_stages = (int)std::min<size_t>(MAX_B_STAGES, left / g.b_stage_bytes);
     g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
+    if (g.b_static) g.b_stages = std::min(g.b_stages, 1);
     if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
     g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
                               sizeof(UmmaShared));
@@ -563,8 +570,6 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const size_t sm = (size_t)c.cin * 27 * c.ncols * sizeof(float);
         const float *wp = (const float *)c.d_wpack;
         auto grid_of = [&](int zt) { return dim3((p.W + 31) / 32, (p.H + 7) / 8, p.N * ((p.D + zt - 1) / zt)); };
-        if (c.ncols == 16)
-        const int zh = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
         const int zh = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
         if (c.ncols == 16)
             stem_conv_kernel<16, 4><<<grid_of(4), 256, sm, st>>>(in, wp, c.cin, p.N, p.D, p.H, p.W, zh, ep);
