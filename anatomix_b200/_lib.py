@@ -32,7 +32,7 @@ EXPORTS = [
     "anx_engine_num_buffers", "anx_engine_buffer_info", "anx_status_string",
     "anx_engine_last_error", "anx_version", "anx_selftest",
     "anx_engine_num_steps", "anx_engine_step_info", "anx_engine_run_steps",
-    "anx_engine_forward_allgather",
+    "anx_engine_forward_allgather", "anx_engine_row_layout",
 ]
 
 
@@ -99,6 +99,8 @@ def load():
     lib.anx_engine_run_steps.restype = i32
     lib.anx_engine_forward_allgather.argtypes = [vp, vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.anx_engine_forward_allgather.restype = i32
+    lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.anx_engine_row_layout.restype = i32
     lib.anx_status_string.argtypes = [i32]
     lib.anx_status_string.restype = C.c_char_p
     lib.anx_engine_last_error.argtypes = [vp]

@@ -180,6 +180,14 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                             const uint32_t dcol = acc + lo * g.ncols;
                             const uint32_t aj = a_lo + j * (HALO_Y * HALO_X);
                             const uint32_t bj = b_lo + (uint32_t)(lo - (j - 2)) * g.ncols;   // first B row, 16 B each
+                            if (g.ablate & 32) {   // timing experiment: 128-byte aligned core matrices (SBO = 128 B)
+                                const uint32_t a_hi_al = (128u >> 4) | (1u << 14);
+                                const uint32_t aj_al = a_lo + j * 176;
+#pragma unroll
+                                for (int t = 0; t < 9; ++t)
+                                    umma_bf16_warp(dcol, make_desc(a_hi_al, aj_al + t * 8), make_desc(b_hi, bj + t * b_tap), idesc);
+                                continue;
+                            }
                             if (g.ablate & 16) {   // timing experiment: every tap reads the aligned brick origin
 #pragma unroll
                                 for (int t = 0; t < 9; ++t)

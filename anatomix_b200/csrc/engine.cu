@@ -138,6 +138,7 @@ struct ShapePlan {            // everything that depends on (N, D, H, W, workspa
 struct anx_engine {
     anx_unet_desc desc;
     int dt = DT_BF16;         // storage type of activations / packed weights
+    int x_lead = 0;           // row layout of the padded planar buffers (layout.cuh layout_of; ANX_X_LEAD)
     int num_sms = 148;
     int max_smem = 0;
     std::vector<ConvLayer> convs;
@@ -334,7 +335,7 @@ bool shape_ok(const anx_engine *e, int n, int d, int h, int w) {
 }
 
 size_t buffer_bytes(const anx_engine *e, const Buffer &b, int n, int d, int h, int w) {
-    const size_t dp = (d >> b.level) + 2, hp = (h >> b.level) + 2, wp = (w >> b.level) + 2;
+    const size_t dp = (d >> b.level) + 2, hp = (h >> b.level) + 2, wp = layout_of(w >> b.level, e->x_lead).pitch;
     return align_up((size_t)n * b.groups * dp * hp * wp * 16, 256);
 }
 
@@ -399,6 +400,9 @@ ActView view_of(const anx_engine *e, const ShapePlan &p, int buf, int group_offs
     v.H = p.H >> b.level;
     v.W = p.W >> b.level;
     v.shell_rep = b.shell_rep;
+    const RowLayout rl = layout_of(v.W, e->x_lead);
+    v.lead = rl.lead;
+    v.pitch = rl.pitch;
     return v;
 }
 
@@ -439,14 +443,16 @@ anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, 
         if (g.smem_bytes > (uint32_t)e->max_smem || g.a_stages < 1 || g.b_stages < 1)
             return e->fail(ANX_ERR_UNSUPPORTED, "conv %d (%d->%d) does not fit shared memory", c.module_index, c.cin,
                            c.cout);
-        // 4-D view of the padded planar buffer: [n*groups][zp][yp][xp*8 + ch]
+        // 4-D view of the padded planar buffer: [n*groups][zp][yp][xp*8 + ch], rows of `pitch` voxels
+        // with the x shell starting `lead` voxels into each row
+        const RowLayout rl = layout_of(w, e->x_lead);
+        const cuuint64_t pitch = (cuuint64_t)rl.pitch;
         cuuint64_t dims[4] = {(cuuint64_t)(w + 2) * 8, (cuuint64_t)(h + 2), (cuuint64_t)(d + 2),
                               (cuuint64_t)N * sb.groups};
-        cuuint64_t strides[3] = {(cuuint64_t)(w + 2) * 16, (cuuint64_t)(w + 2) * (h + 2) * 16,
-                                 (cuuint64_t)(w + 2) * (h + 2) * (d + 2) * 16};
+        cuuint64_t strides[3] = {pitch * 16, pitch * (h + 2) * 16, pitch * (h + 2) * (d + 2) * 16};
         cuuint32_t box[4] = {HALO_X * 8, HALO_Y, (cuuint32_t)(g.bz + 2), 2};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        void *base = static_cast<char *>(workspace) + p->buf_offset[c.src_buf];
+        void *base = static_cast<char *>(workspace) + p->buf_offset[c.src_buf] + (size_t)rl.lead * 16;
         CUresult r = encode(&p->tmaps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -497,6 +503,7 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         ep.dst.groups_total = 0;
         ep.dst.group_offset = 0;
         ep.dst.D = p.D; ep.dst.H = p.H; ep.dst.W = p.W;
+        ep.dst.lead = 0; ep.dst.pitch = p.W;
     } else {
         ep.mode = OUT_PADDED_BF16;
         ep.dst = view_of(e, p, c.dst_buf, c.dst_group_offset);
@@ -712,6 +719,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (desc->flags & ANX_FLAG_STORE_BF16) e->dt = DT_BF16;
     e->num_sms = prop.multiProcessorCount;
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (const char *xl = getenv("ANX_X_LEAD")) e->x_lead = atoi(xl);
     build_program(e);
     for (auto &c : e->convs) {
         c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
@@ -928,6 +936,14 @@ anx_status anx_engine_buffer_info(const anx_engine *e, int32_t n, int32_t d, int
     if (bytes) *bytes = buffer_bytes(e, e->bufs[index], n, d, h, w);
     if (level) *level = e->bufs[index].level;
     if (groups) *groups = e->bufs[index].groups;
+    return ANX_OK;
+}
+
+anx_status anx_engine_row_layout(const anx_engine *e, int32_t w, int32_t *lead, int32_t *pitch) {
+    if (!e || w < 1) return ANX_ERR_BAD_ARG;
+    const RowLayout rl = layout_of(w, e->x_lead);
+    if (lead) *lead = rl.lead;
+    if (pitch) *pitch = rl.pitch;
     return ANX_OK;
 }
 

@@ -119,7 +119,7 @@ __device__ __forceinline__ int mirror_delta(int v, int S, int rep = 0) {
 // group g0 into a padded planar buffer, including its reflect-shell copies.
 __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, int g0, int ngroups, int z, int y,
                                                     int x, const uint4 &q0, const uint4 &q1) {
-    const size_t row = (size_t)(dst.W + 2), plane = row * (dst.H + 2), gstride = plane * (dst.D + 2);
+    const size_t row = (size_t)dst.pitch, plane = row * (dst.H + 2), gstride = plane * (dst.D + 2);
     uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
     if (dst.D >= 4 && dst.H >= 4 && dst.W >= 4) {
         const int dz = mirror_delta(z, dst.D, dst.shell_rep), dy = mirror_delta(y, dst.H, dst.shell_rep),

@@ -3,7 +3,16 @@
 // Every intermediate activation lives in a reflect-PADDED, channel-group-planar
 // bf16 buffer:
 //
-//      [n][g][zp][yp][xp][8]      zp in [0, D+2), yp in [0, H+2), xp in [0, W+2)
+//      [n][g][zp][yp][lead + xp][8]      zp in [0, D+2), yp in [0, H+2), xp in [0, W+2)
+//
+// with `pitch` voxels per row and `lead` unused voxels in front of the x shell.  The default is the dense
+// form (lead 0, pitch W + 2).  With lead 1 (pitch W + 4) interior voxel x = 0 sits on a 32-byte sector
+// boundary and an 8-voxel tile row stored by the conv epilogue is four FULL sectors instead of three full
+// and two half ones; lead 7 aligns tile rows to 128-byte lines.  The epilogue's store pattern ALONE drains
+// at 2.7 / 5.7 / 5.3 TB/s for lead 0 / 1 / 7 (tools/micro/store_bw.cu on B200), but inside the conv kernel
+// the stores hide behind the MMA stream and the halo-brick loads grow from 5 to 6 sectors per row, so the
+// whole forward measured 2080 / 2060 / 2070 volumes/s on one box: the variants stay selectable
+// (ANX_X_LEAD) for kernels whose MMA phase gets short enough to expose the stores.
 //
 // g indexes groups of 8 channels (16 bytes per voxel per group).  The one-voxel
 // shell holds the reflect padding of nn.Conv3d(padding_mode='reflect')
@@ -23,14 +32,24 @@
 
 namespace anx {
 
+// Row geometry of a padded planar buffer of interior width W for a given lead (host side picks the lead).
+struct RowLayout { int lead, pitch; };
+__host__ __device__ __forceinline__ RowLayout layout_of(int W, int lead) {
+    if (lead <= 0) return RowLayout{0, W + 2};
+    if (lead == 1) return RowLayout{1, (W + 4) & ~1};
+    return RowLayout{7, (W + 16) & ~7};
+}
+
 struct ActView {            // one tensor inside a padded planar buffer
     __nv_bfloat16 *base;    // start of the whole buffer
     int groups_total;       // channel groups per sample in the buffer
     int group_offset;       // first group of this tensor
     int D, H, W;            // interior size
     int shell_rep;          // shell semantics written by the producer: 0 reflect (x[1] / x[S-2]), 1 replicate (x[0] / x[S-1])
+    int lead, pitch;        // row geometry: voxels in front of the x shell, voxels per row (layout_of)
     __host__ __device__ __forceinline__ size_t voxel_index(int n, int g, int zp, int yp, int xp) const {
-        return ((((size_t)n * groups_total + (group_offset + g)) * (D + 2) + zp) * (H + 2) + yp) * (size_t)(W + 2) + xp;
+        return ((((size_t)n * groups_total + (group_offset + g)) * (D + 2) + zp) * (H + 2) + yp) * (size_t)pitch +
+               lead + xp;
     }
     __host__ __device__ __forceinline__ uint4 *at(int n, int g, int zp, int yp, int xp) const {
         return reinterpret_cast<uint4 *>(base) + voxel_index(n, g, zp, yp, xp);

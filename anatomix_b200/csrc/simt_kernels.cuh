@@ -273,13 +273,16 @@ inorm_act_kernel(ActView t, int groups, const double *__restrict__ stats, int st
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mean[i] = s_mean[i]; rstd[i] = s_rstd[i]; }
     const size_t count = (size_t)(t.D + 2) * (t.H + 2) * (t.W + 2);
+    const unsigned wp = (unsigned)(t.W + 2), pitch = (unsigned)t.pitch;
     uint4 *base = t.at(n, gidx, 0, 0, 0);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / wp;
+        uint4 *cell = base + row * pitch + (i - row * wp);      // rows carry unused lead / tail voxels
         float v[8];
-        unpack_x8(base[i], v, dt);
+        unpack_x8(*cell, v, dt);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = activate((v[k] - mean[k]) * rstd[k], act, slope);
-        base[i] = pack_x8(v, dt);
+        *cell = pack_x8(v, dt);
     }
 }
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                                                    const float *seed, int half, int bz, int ncols, int D,
                                                    const EpiTile &next, bool next_valid) {
     const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
-    const size_t plane = (size_t)(Hh + 2) * (Ww + 2);          // uint4 units
+    const size_t plane = (size_t)(Hh + 2) * ep.dst.pitch;      // uint4 units
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
     constexpr bool SEEDED = MODE == EPI_SEEDED;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
     const int rep = ep.dst.shell_rep;
     const int mdx = mirror_delta(t.x, Ww, rep), mdy = mirror_delta(t.y, Hh, rep);
-    const size_t rowp = (size_t)(Ww + 2);
+    const size_t rowp = (size_t)ep.dst.pitch;
     uint4 *pbase = nullptr;
     float *fbase = nullptr;
     if constexpr (PADDED)
@@ -185,7 +185,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
         };
         if (SEEDED) {
             s_xy = next_valid && next.in_xy;
-            splane = (size_t)(ep.seed_src.H + 2) * (ep.seed_src.W + 2);
+            splane = (size_t)(ep.seed_src.H + 2) * ep.seed_src.pitch;
             sgroup = splane * (ep.seed_src.D + 2);
             sbase = seed_ptr(ep, next, 0, 0);
             seed_load(plane_lo(half, bz), nq0, nq1);
@@ -234,7 +234,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                         uint4 *p = ep.dst.at(t.n, co0 >> 3, 2 * z + ((par >> 2) & 1) + 1, 2 * t.y + ((par >> 1) & 1) + 1,
                                              2 * t.x + (par & 1) + 1);
                         *p = q0;
-                        p[(size_t)(Dd + 2) * (Hh + 2) * (Ww + 2)] = q1;
+                        p[gstride] = q1;
                     } else if (big) {
                         uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
                         *p = q0;

@@ -126,7 +126,9 @@ class Engine:
                 raise self._shape_error((n, self.input_nc, d, h, w))
             if len(self._workspaces) >= 4:
                 self._workspaces.pop(next(iter(self._workspaces)))
-            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            # zeroed once: the unused lead / tail voxels of every padded row then stay finite and equal
+            # between runs (halo plane exchanges and buffer dumps copy them along)
+            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
             self._workspaces[key] = ws
         return ws
 
@@ -212,6 +214,12 @@ class Engine:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self._check(self.lib.anx_engine_run_steps(
                 self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, first, last))
+
+    def row_layout(self, w: int):
+        """(lead, pitch) of a padded planar row of interior width ``w`` (anx_engine_row_layout)."""
+        lead, pitch = C.c_int32(), C.c_int32()
+        self._check(self.lib.anx_engine_row_layout(self._h, w, C.byref(lead), C.byref(pitch)))
+        return lead.value, pitch.value
 
     def buffer_table(self, n, d, h, w):
         """[(offset, bytes, level, groups)] of the workspace's activation buffers."""

@@ -57,7 +57,7 @@ class DepthSlabExtractor:
     def _exchange(self, ws, table, buf, goff, groups, n, d, h, w):
         off, nbytes, level, gtot = table[buf]
         dl, hl, wl = d >> level, h >> level, w >> level
-        plane = (hl + 2) * (wl + 2) * 16
+        plane = (hl + 2) * self.engine.row_layout(wl)[1] * 16      # whole padded rows, lead / tail voxels included
         view = ws[off:off + n * gtot * (dl + 2) * plane].view(n, gtot, dl + 2, plane)[:, goff:goff + groups]
         lo_out, hi_out = view[:, :, 1].contiguous(), view[:, :, dl].contiguous()
         lo_in, hi_in = torch.empty_like(lo_out), torch.empty_like(hi_out)

@@ -171,13 +171,18 @@ anx_status anx_engine_profile(anx_engine *engine, const float *in_ncdhw, float *
                               float *ms_out, char (*names_out)[32], int32_t capacity,
                               int32_t *count);
 
-/* Introspection of the workspace layout (tests / debugging): activation buffer
- * `index` holds `groups` 8-channel groups of a reflect-padded planar bf16 tensor
- * [n][g][D/2^level+2][H/2^level+2][W/2^level+2][8] at `offset` in the workspace. */
+/* Introspection of the workspace layout (tests / debugging / the depth-slab halo exchange):
+ * activation buffer `index` holds `groups` 8-channel groups of a reflect-padded planar
+ * 16-bit tensor [n][g][D/2^level+2][H/2^level+2][pitch][8] at `offset` in the workspace;
+ * anx_engine_row_layout gives, for an interior width w = W/2^level, the `pitch` (voxels per
+ * row) and the `lead`: voxels [lead, lead + w + 2) of a row are the x shell + interior (the
+ * lead keeps interior rows on 32-byte sector boundaries; lead / tail voxels are never read). */
 int32_t anx_engine_num_buffers(const anx_engine *engine);
 anx_status anx_engine_buffer_info(const anx_engine *engine, int32_t n, int32_t d, int32_t h,
                                   int32_t w, int32_t index, size_t *offset, size_t *bytes,
                                   int32_t *level, int32_t *groups);
+
+anx_status anx_engine_row_layout(const anx_engine *engine, int32_t w, int32_t *lead, int32_t *pitch);
 
 const char *anx_status_string(anx_status status);
 /* Detail of the last failure on this engine (thread-unsafe convenience). */

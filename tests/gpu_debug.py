@@ -45,6 +45,14 @@ def to_padded_planar(t):
     return p.view(n, c // 8, 8, d, h, w).permute(0, 1, 3, 4, 5, 2).contiguous()
 
 
+def read_padded(eng, ws, off, shape, dtype):
+    """[N, G, D+2, H+2, W+2, 8] view of a padded planar buffer (rows carry lead / tail voxels)."""
+    n, g, dp, hp, wp, _ = shape
+    lead, pitch = eng.row_layout(wp - 2)
+    t = ws[off:off + n * g * dp * hp * pitch * 16].view(dtype).float().cpu().view(n, g, dp, hp, pitch, 8)
+    return t[:, :, :, :, lead:lead + wp].contiguous()
+
+
 def compare(eng, cfg, state, x, emulate=True):
     n, _, d, h, w = x.shape
     prods = buffer_producers(cfg)
@@ -57,7 +65,7 @@ def compare(eng, cfg, state, x, emulate=True):
     for buf, idx, _ in prods:
         off, nb, lvl, grp = table[buf]
         want = to_padded_planar(tap[idx])
-        got = ws[off:off + want.numel() * 2].view(O.engine_storage_dtype(cfg)).float().cpu().view(want.shape)
+        got = read_padded(eng, ws, off, want.shape, O.engine_storage_dtype(cfg))
         inner = (slice(None), slice(None), slice(1, -1), slice(1, -1), slice(1, -1))
         den = want.norm().clamp_min(1e-20)
         rel_all = ((got - want).norm() / den).item()
@@ -96,8 +104,7 @@ def main():
     def planar(buf, groups_total, dims):
         off, nb, lvl, grp = table[buf]
         dd, hh, ww = dims
-        t = ws[off:off + n * groups_total * (dd + 2) * (hh + 2) * (ww + 2) * 16].view(torch.bfloat16).float().cpu()
-        return t.view(n, groups_total, dd + 2, hh + 2, ww + 2, 8)
+        return read_padded(eng, ws, off, (n, groups_total, dd + 2, hh + 2, ww + 2, 8), torch.bfloat16)
     cat0 = planar(0, 3 * a.ngf // 8, (d, h, w))[:, :a.ngf // 8]
     got8 = cat0.permute(0, 1, 5, 2, 3, 4).reshape(n, a.ngf, d + 2, h + 2, w + 2)[:, :, 1:-1, 1:-1, 1:-1]
     for name, got, want in (("conv8", got8, taps[1]),):
