@@ -32,7 +32,8 @@ EXPORTS = [
     "anx_engine_num_buffers", "anx_engine_buffer_info", "anx_status_string",
     "anx_engine_last_error", "anx_version", "anx_selftest",
     "anx_engine_num_steps", "anx_engine_step_info", "anx_engine_run_steps",
-    "anx_engine_forward_allgather", "anx_engine_row_layout",
+    "anx_engine_forward_allgather", "anx_engine_row_layout", "anx_engine_set_head", "anx_engine_out_channels",
+    "anx_engine_num_taps", "anx_engine_tap_info", "anx_engine_export_tap", "anx_avgpool3d_scale_f32",
 ]
 
 
@@ -101,6 +102,18 @@ def load():
     lib.anx_engine_forward_allgather.restype = i32
     lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_row_layout.restype = i32
+    lib.anx_engine_set_head.argtypes = [vp, i32, vp, vp, i32]
+    lib.anx_engine_set_head.restype = i32
+    lib.anx_engine_out_channels.argtypes = [vp]
+    lib.anx_engine_out_channels.restype = i32
+    lib.anx_engine_num_taps.argtypes = [vp]
+    lib.anx_engine_num_taps.restype = i32
+    lib.anx_engine_tap_info.argtypes = [vp, i32] + [C.POINTER(i32)] * 5
+    lib.anx_engine_tap_info.restype = i32
+    lib.anx_engine_export_tap.argtypes = [vp, i32, i32, i32, i32, i32, vp, sz, vp, vp]
+    lib.anx_engine_export_tap.restype = i32
+    lib.anx_avgpool3d_scale_f32.argtypes = [vp, vp, C.c_int64, i32, i32, i32, i32, C.c_float, vp]
+    lib.anx_avgpool3d_scale_f32.restype = i32
     lib.anx_status_string.argtypes = [i32]
     lib.anx_status_string.restype = C.c_char_p
     lib.anx_engine_last_error.argtypes = [vp]

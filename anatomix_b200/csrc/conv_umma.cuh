@@ -97,6 +97,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         tmem_relinquish();
     }
     for (int i = threadIdx.x; i < g.ncols * g.n_splits; i += blockDim.x) sh->shift[i] = ep.bias[i];
+    if constexpr (MODE == EPI_F32_HEAD)   // ncols <= 32 here: the head sits behind the channel shift
+        for (int i = threadIdx.x; i < HEAD_FLOATS; i += blockDim.x) sh->shift[HEAD_SMEM_OFFSET + i] = ep.head[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -115,7 +115,18 @@ struct Step {
     int conv = -1;                    // STEP_STEM / STEP_CONV
     int src_buf = -1, dst_buf = -1;   // STEP_POOL / STEP_UP
     int groups = 0, dst_group_offset = 0;
+    int module_index = -1;            // STEP_POOL / STEP_UP: position of the nn.MaxPool3d / nn.Upsample slot
     char name[32];
+};
+
+// A feature tap (reference network.py:475-529, `forward(layers=[...])`): the activation that exists after
+// Sequential slot `module_index`, when the engine materialises it (post-activation conv outputs, pooled
+// tensors, the [skip | upsampled] concat after an Upsample slot, the network output).
+struct TapSite {
+    int module_index;
+    int buffer, group_offset, groups;   // buffer -1: the network output
+    int channels, level;
+    int last_step;                      // the tensor is complete once steps [0, last_step] have run
 };
 
 struct GatherArgs {           // fused all-gather destinations of the final conv (one forward call)
@@ -145,6 +156,10 @@ struct anx_engine {
     std::vector<Logical> logical;
     std::vector<Buffer> bufs;
     std::vector<Step> steps;
+    std::vector<TapSite> taps;
+    // optional linear head fused into the last conv's epilogue (anx_engine_set_head)
+    int head_nc = 0;
+    float *d_head = nullptr;          // [HEAD_MAX][16] weights then [HEAD_MAX] bias
     std::mutex mu;
     std::vector<std::shared_ptr<ShapePlan>> plans;
     // host-buffer pipeline (anx_engine_forward_host): copy streams and fork/join events
@@ -246,6 +261,7 @@ void build_program(anx_engine *e) {
         s.src_buf = cat[i];
         s.dst_buf = p;
         s.groups = width[i] / 8;
+        s.module_index = mi;
         snprintf(s.name, sizeof s.name, "pool%d_L%d", mi, i);
         e->steps.push_back(s);
         mi += 1;
@@ -311,6 +327,7 @@ void build_program(anx_engine *e) {
         s.dst_buf = cat[l];
         s.groups = width[l + 1] / 8;
         s.dst_group_offset = width[l] / 8;
+        s.module_index = mi;
         snprintf(s.name, sizeof s.name, "up%d_L%d", mi, l);
         e->steps.push_back(s);
         mi += 1;
@@ -325,6 +342,39 @@ void build_program(anx_engine *e) {
         const int P = add_buffer(e, e->convs[pr.second].level, e->convs[pr.second].cout);
         e->convs[pr.first].dst_buf = P;
         e->convs[pr.second].seed_buf = P;
+    }
+}
+
+// Which Sequential slots leave a tensor the engine actually stores (see TapSite).
+void build_taps(anx_engine *e) {
+    e->taps.clear();
+    for (int si = 0; si < (int)e->steps.size(); ++si) {
+        const Step &s = e->steps[si];
+        if (s.kind == STEP_STEM || s.kind == STEP_CONV) {
+            const ConvLayer &c = e->convs[s.conv];
+            if (c.d2s_cout) continue;            // partial sums of a split decoder conv: not a network tensor
+            int last = si;
+            if (c.inorm) last = si + 1;          // the STEP_NORM that follows normalises + activates in place
+            if (c.is_final) {
+                e->taps.push_back(TapSite{c.module_index, -1, 0, (c.cout + 7) / 8, c.cout, 0, last});
+                continue;
+            }
+            // the stored tensor is the conv's output after norm and activation: the tap of the LAST slot of
+            // the conv block (act if present, else norm, else the conv itself)
+            const int idx = c.module_index + (c.has_norm ? 1 : 0) + (c.has_act ? 1 : 0);
+            e->taps.push_back(TapSite{idx, c.dst_buf, c.dst_group_offset, c.cout / 8, c.cout, c.level, last});
+            // The reference's activations are in-place modules (network.py:171-204): the tensor tapped at the
+            // slot just before the activation is overwritten by it, so that tap holds the same values.
+            if (c.has_act)
+                e->taps.push_back(TapSite{idx - 1, c.dst_buf, c.dst_group_offset, c.cout / 8, c.cout, c.level, last});
+        } else if (s.kind == STEP_POOL) {
+            const Buffer &b = e->bufs[s.dst_buf];
+            e->taps.push_back(TapSite{s.module_index, s.dst_buf, 0, s.groups, s.groups * 8, b.level, si});
+        } else if (s.kind == STEP_UP) {
+            // reference network.py:545: the tap after an Upsample slot sees cat(skip, upsampled)
+            const Buffer &b = e->bufs[s.dst_buf];
+            e->taps.push_back(TapSite{s.module_index, s.dst_buf, 0, b.groups, b.groups * 8, b.level, si});
+        }
     }
 }
 
@@ -479,6 +529,12 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         ep.pool_kind = e->desc.pool_kind;
         ep.pool_dst = view_of(e, p, c.pool_dst_buf, 0);
     }
+    ep.head_nc = 0;
+    ep.head = nullptr;
+    if (c.is_final && e->head_nc > 0) {
+        ep.head_nc = e->head_nc;
+        ep.head = e->d_head;
+    }
     if (ga && c.is_final) {
         for (int i = 0; i < ga->n_peers; ++i) ep.out_peers[i] = ga->peers[i];
         ep.n_peers = ga->n_peers;
@@ -592,6 +648,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const ConvLayer &c = e->convs[s.conv];
         const ConvGeom &g = p.geoms[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
+        if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0))
+            return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path without a fused gather");
         if (force_simt) {
             ActView src = view_of(e, p, c.src_buf, 0);
             const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
@@ -601,7 +659,11 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const int grid = std::min(g.total_tiles, e->num_sms);
             const uint8_t *wp_ = (const uint8_t *)c.d_wpack;
 #define ANX_CONV(MODE_) conv3_umma_kernel<MODE_><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g, wp_, ep)
-            if (ep.mode == OUT_NCDHW_F32) { if (ep.n_peers > 0) ANX_CONV(EPI_F32_PEERS); else ANX_CONV(EPI_F32); }
+            if (ep.mode == OUT_NCDHW_F32) {
+                if (ep.n_peers > 0) ANX_CONV(EPI_F32_PEERS);
+                else if (ep.head_nc > 0) ANX_CONV(EPI_F32_HEAD);
+                else ANX_CONV(EPI_F32);
+            }
             else if (ep.seed_on) ANX_CONV(EPI_SEEDED);
             else if (ep.stats) ANX_CONV(EPI_STATS);
             else if (ep.d2s_cout) ANX_CONV(EPI_D2S);
@@ -721,6 +783,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
     if (const char *xl = getenv("ANX_X_LEAD")) e->x_lead = atoi(xl);
     build_program(e);
+    build_taps(e);
     for (auto &c : e->convs) {
         c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
@@ -729,7 +792,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
 #define ANX_SMEM(K_) if (err == cudaSuccess) err = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem)
     ANX_SMEM(conv3_umma_kernel<EPI_PADDED>); ANX_SMEM(conv3_umma_kernel<EPI_POOL>); ANX_SMEM(conv3_umma_kernel<EPI_D2S>);
     ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
-    ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>);
+    ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
     ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
 #undef ANX_SMEM
@@ -753,6 +816,7 @@ void anx_engine_destroy(anx_engine *e) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
+    if (e->d_head) cudaFree(e->d_head);
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
@@ -1073,7 +1137,8 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
     // chunk i-1 run on their own streams while chunk i computes on the caller's stream.  The
     // download (output_nc/input_nc times larger than the upload) is what bounds the call.
     const int chunks = std::min(n, 4);
-    const size_t in_vol = (size_t)d * h * w * e->desc.input_nc, out_vol = (size_t)d * h * w * e->desc.output_nc;
+    const size_t in_vol = (size_t)d * h * w * e->desc.input_nc,
+                 out_vol = (size_t)d * h * w * anx_engine_out_channels(e);
     ANX_CUDA(e, cudaEventRecord(e->ev_fork, st));
     ANX_CUDA(e, cudaStreamWaitEvent(e->h2d_stream, e->ev_fork, 0));
     ANX_CUDA(e, cudaStreamWaitEvent(e->d2h_stream, e->ev_fork, 0));
@@ -1096,6 +1161,86 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
     ANX_CUDA(e, cudaEventRecord(e->ev_join, e->d2h_stream));
     ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));   // the caller's stream completes after the last download
     return ANX_OK;
+}
+
+int32_t anx_engine_out_channels(const anx_engine *e) {
+    if (!e) return -1;
+    return e->head_nc > 0 ? e->head_nc : e->desc.output_nc;
+}
+
+anx_status anx_engine_set_head(anx_engine *e, int32_t head_nc, const float *weight, const float *bias,
+                               int32_t location) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (head_nc == 0) {            // back to the plain network output
+        e->head_nc = 0;
+        return ANX_OK;
+    }
+    if (head_nc < 0 || head_nc > HEAD_MAX || !weight) return e->fail(ANX_ERR_BAD_ARG, "head of %d channels (1..%d)", head_nc, HEAD_MAX);
+    if (e->desc.output_nc > 16)
+        return e->fail(ANX_ERR_UNSUPPORTED, "a fused head needs output_nc <= 16 (one accumulator chunk per voxel)");
+    if (e->desc.flags & ANX_FLAG_FORCE_SIMT) return e->fail(ANX_ERR_UNSUPPORTED, "no fused head on the CUDA-core debug path");
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    const int cin = e->desc.output_nc;
+    std::vector<float> hw((size_t)head_nc * cin), hb(head_nc, 0.0f), img(HEAD_FLOATS, 0.0f);
+    const cudaMemcpyKind kind = location == ANX_LOC_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    ANX_CUDA(e, cudaMemcpy(hw.data(), weight, hw.size() * sizeof(float), kind));
+    if (bias) ANX_CUDA(e, cudaMemcpy(hb.data(), bias, hb.size() * sizeof(float), kind));
+    for (int k = 0; k < head_nc; ++k) {
+        img[k] = hb[k];
+        for (int c = 0; c < cin; ++c) img[HEAD_MAX + k * 16 + c] = hw[(size_t)k * cin + c];
+    }
+    if (!e->d_head) ANX_CUDA(e, cudaMalloc(&e->d_head, HEAD_FLOATS * sizeof(float)));
+    ANX_CUDA(e, cudaMemcpy(e->d_head, img.data(), HEAD_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    e->head_nc = head_nc;
+    return ANX_OK;
+}
+
+int32_t anx_engine_num_taps(const anx_engine *e) { return e ? (int32_t)e->taps.size() : -1; }
+
+anx_status anx_engine_tap_info(const anx_engine *e, int32_t k, int32_t *module_index, int32_t *channels,
+                               int32_t *level, int32_t *last_step, int32_t *is_output) {
+    if (!e || k < 0 || k >= (int)e->taps.size()) return ANX_ERR_BAD_ARG;
+    const TapSite &t = e->taps[k];
+    if (module_index) *module_index = t.module_index;
+    if (channels) *channels = t.channels;
+    if (level) *level = t.level;
+    if (last_step) *last_step = t.last_step;
+    if (is_output) *is_output = t.buffer < 0 ? 1 : 0;
+    return ANX_OK;
+}
+
+anx_status anx_engine_export_tap(anx_engine *e, int32_t k, int32_t n, int32_t d, int32_t h, int32_t w,
+                                 void *workspace, size_t ws_bytes, float *out, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (k < 0 || k >= (int)e->taps.size() || !out) return e->fail(ANX_ERR_BAD_ARG, "bad tap ordinal or null output");
+    const TapSite &t = e->taps[k];
+    if (t.buffer < 0) return e->fail(ANX_ERR_BAD_ARG, "tap %d is the network output: it is already fp32 NCDHW", k);
+    if (!shape_ok(e, n, d, h, w)) return e->fail(ANX_ERR_BAD_SHAPE, "bad shape for a tap export");
+    const size_t need = anx_engine_workspace_bytes(e, n, d, h, w);
+    if (!workspace || ws_bytes < need) return e->fail(ANX_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", ws_bytes, need);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    anx_status st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    ActView src = view_of(e, *p, t.buffer, t.group_offset);
+    const size_t items = (size_t)n * t.groups * src.D * src.H * src.W;
+    export_ncdhw_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, n, t.groups, t.channels, out, e->dt);
+    ANX_CUDA(e, cudaGetLastError());
+    return ANX_OK;
+}
+
+anx_status anx_avgpool3d_scale_f32(const float *in, float *out, int64_t nc, int32_t d, int32_t h, int32_t w,
+                                   int32_t k, float scale, void *stream) {
+    if (!in || !out || nc < 1 || k < 1 || d < k || h < k || w < k) return ANX_ERR_BAD_ARG;
+    if (k == 2 && ((w & 1) || (reinterpret_cast<uintptr_t>(in) & 7))) return ANX_ERR_BAD_ARG;   // float2 loads
+    const size_t items = (size_t)nc * (d / k) * (h / k) * (w / k);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    avgpool3d_scale_kernel<<<grid_for(items, 256, sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, (size_t)nc, d, h, w, k, scale);
+    return cudaGetLastError() == cudaSuccess ? ANX_OK : ANX_ERR_CUDA;
 }
 
 anx_status anx_engine_profile(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h, int32_t w,

@@ -93,7 +93,14 @@ struct Epilogue {
     // the partial sums written by the depth-to-space launch.
     int seed_on;
     ActView seed_src;
+    // Linear head fused behind the last conv (OUT_NCDHW_F32, cout <= 16): out[k] = head[k] + sum_c
+    // head[HEAD_MAX + k*16 + c] * y[c] for k < head_nc, written as fp32 [N, head_nc, D, H, W].
+    int head_nc;
+    const float *head;      // device: [HEAD_MAX] bias then [HEAD_MAX][16] weights
 };
+
+constexpr int HEAD_MAX = 32;                            // most output channels a fused head may have
+constexpr int HEAD_FLOATS = HEAD_MAX + HEAD_MAX * 16;   // bias + weights
 
 // tile geometry of the tensor-core conv: 8 (x) x 16 (y) voxels per MMA (M = 128),
 // `bz` output planes per CTA tile.

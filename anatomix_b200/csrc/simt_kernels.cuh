@@ -248,6 +248,62 @@ upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt) 
     }
 }
 
+// ------------------------------------------------------------------ tap export
+// One stored tensor (padded planar 16-bit) -> fp32 NCDHW, for `forward(layers=[...])` feature taps
+// (reference network.py:475-529).  One thread per (n, group, z, y, x), lanes along x: a warp reads 512
+// contiguous bytes and writes eight 128-byte runs.
+__global__ void __launch_bounds__(256)
+export_ncdhw_kernel(ActView src, int N, int groups, int channels, float *__restrict__ out, int dt) {
+    const size_t vol = (size_t)src.D * src.H * src.W;
+    const size_t total = (size_t)N * groups * vol;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+        size_t v = id;
+        const int x = (int)(v % src.W); v /= src.W;
+        const int y = (int)(v % src.H); v /= src.H;
+        const int z = (int)(v % src.D); v /= src.D;
+        const int gidx = (int)(v % groups);
+        const int n = (int)(v / groups);
+        float f[8];
+        unpack_x8(*src.at(n, gidx, z + 1, y + 1, x + 1), f, dt);
+        float *o = out + ((size_t)n * channels + gidx * 8) * vol + ((size_t)z * src.H + y) * src.W + x;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (gidx * 8 + i < channels) o[(size_t)i * vol] = f[i];
+    }
+}
+
+// ------------------------------------------------------- scaled average pooling
+// out = scale * avg_pool3d(in, k, stride=k) on fp32 [NC, D, H, W] (floor mode): the feature post-processing
+// of the registration caller (reference run_convex_adam_with_network_feats.py:166-167, 198-205).  One
+// thread per output voxel, lanes along x; streaming, HBM-bound (reads every input byte once).
+__global__ void __launch_bounds__(256)
+avgpool3d_scale_kernel(const float *__restrict__ in, float *__restrict__ out, size_t NC, int D, int H, int W, int k,
+                       float scale) {
+    const int Do = D / k, Ho = H / k, Wo = W / k;
+    const size_t total = NC * Do * Ho * Wo;
+    const float norm = scale / (float)(k * k * k);
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+        size_t v = id;
+        const int x = (int)(v % Wo); v /= Wo;
+        const int y = (int)(v % Ho); v /= Ho;
+        const int z = (int)(v % Do);
+        const size_t nc = v / Do;
+        const float *src = in + ((nc * D + (size_t)z * k) * H + (size_t)y * k) * W + (size_t)x * k;
+        float a = 0.0f;
+        for (int dz = 0; dz < k; ++dz)
+            for (int dy = 0; dy < k; ++dy) {
+                const float *row = src + ((size_t)dz * H + dy) * W;
+                if (k == 2) {
+                    const float2 p = __ldg(reinterpret_cast<const float2 *>(row));   // x*k even, W even when k == 2 divides it
+                    a += p.x + p.y;
+                } else {
+                    for (int dx = 0; dx < k; ++dx) a += __ldg(row + dx);
+                }
+            }
+        out[id] = a * norm;
+    }
+}
+
 // ---------------------------------------------------------- instance norm + act
 // In place over one tensor inside a padded planar buffer, shell included (the shell
 // holds mirror copies, so normalising it element-wise equals mirroring afterwards):

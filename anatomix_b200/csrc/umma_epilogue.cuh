@@ -57,8 +57,10 @@ enum EpiMode : int {
     EPI_STATS = 3,       // ... raw output + instance-norm sums
     EPI_F32 = 4,         // fp32 NCDHW network output
     EPI_F32_PEERS = 5,   // ... into every peer's gather buffer
-    EPI_SEEDED = 6       // padded store, accumulators re-seeded from stored partial sums
+    EPI_SEEDED = 6,      // padded store, accumulators re-seeded from stored partial sums
+    EPI_F32_HEAD = 7     // fp32 NCDHW output of a linear head applied to the conv's 16 channels
 };
+constexpr int HEAD_SMEM_OFFSET = 32;   // floats behind the channel shift in shared memory where the head lives
 
 // `next` / `next_valid`: the tile that will reuse this accumulator stage (seeded kernels only).
 template <int MODE>
@@ -70,7 +72,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
     constexpr bool SEEDED = MODE == EPI_SEEDED;
-    constexpr bool PADDED = MODE != EPI_F32 && MODE != EPI_F32_PEERS;
+    constexpr bool PADDED = MODE != EPI_F32 && MODE != EPI_F32_PEERS && MODE != EPI_F32_HEAD;
     const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
     const int rep = ep.dst.shell_rep;
     const int mdx = mirror_delta(t.x, Ww, rep), mdy = mirror_delta(t.y, Hh, rep);
@@ -252,6 +254,23 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                } else if constexpr (MODE == EPI_F32_HEAD) {
+                    // 1x1x1 conv on the voxel's channel vector (registers) with the head in shared memory
+                    const float *hb = seed + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
+                    float *o = ep.out_f32 + (size_t)t.n * ep.head_nc * vol + ((size_t)z * Hh + t.y) * Ww + t.x;
+#pragma unroll 2
+                    for (int k = 0; k < ep.head_nc; ++k) {
+                        float a = hb[k];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w4 = reinterpret_cast<const float4 *>(hw + k * 16)[i];
+                            a = fmaf(w4.x, v[4 * i], a);
+                            a = fmaf(w4.y, v[4 * i + 1], a);
+                            a = fmaf(w4.z, v[4 * i + 2], a);
+                            a = fmaf(w4.w, v[4 * i + 3], a);
+                        }
+                        o[(size_t)k * vol] = a;
+                    }
                 } else {
                     // fused all-gather: the same values go to every rank's gather buffer over NVLink
                     const size_t off = ((size_t)(ep.sample_offset + t.n) * ep.cout + c0) * vol +

@@ -52,8 +52,9 @@ class Engine:
             st = self.lib.anx_engine_create(C.byref(desc), C.byref(self._h))
         if st != _lib.ANX_OK:
             raise EngineError(st, self.lib.anx_status_string(st).decode())
-        self.output_nc = cfg["output_nc"]
+        self.output_nc = cfg["output_nc"]      # channels a forward writes (a fused head changes it)
         self.input_nc = cfg["input_nc"]
+        self.flags = flags
         self._workspaces: Dict[tuple, torch.Tensor] = {}
 
     # -- lifetime ----------------------------------------------------------
@@ -103,6 +104,61 @@ class Engine:
             ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
             with torch.cuda.device(self.device):
                 self._check(self.lib.anx_engine_set_conv(self._h, k, ptr(w), ptr(b), *[ptr(t) for t in bn], 0))
+
+    def set_head(self, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor] = None):
+        """Fuses a 1x1x1 conv ``[K, output_nc(,1,1,1)]`` (+ bias) into the last conv's epilogue
+        (anx_engine_set_head); ``None`` removes it.  Forwards then return ``[N, K, D, H, W]``."""
+        if weight is None:
+            self._check(self.lib.anx_engine_set_head(self._h, 0, None, None, 0))
+        else:
+            w = weight.detach().to("cpu", torch.float32).reshape(weight.shape[0], -1).contiguous()
+            if w.shape[1] != self.cfg["output_nc"]:
+                raise ValueError(f"head weight has {w.shape[1]} input channels, the network outputs {self.cfg['output_nc']}")
+            b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
+            with torch.cuda.device(self.device):
+                self._check(self.lib.anx_engine_set_head(
+                    self._h, w.shape[0], C.c_void_p(w.data_ptr()), None if b is None else C.c_void_p(b.data_ptr()), 0))
+        self.output_nc = self.lib.anx_engine_out_channels(self._h)
+
+    # -- feature taps ------------------------------------------------------------
+    def tap_table(self):
+        """{module_index: (ordinal, channels, level, last_step, is_output)} of the tensors the engine
+        can hand out for ``forward(layers=[...])`` (anx_engine_tap_info)."""
+        out = {}
+        for k in range(self.lib.anx_engine_num_taps(self._h)):
+            v = [C.c_int32() for _ in range(5)]
+            self._check(self.lib.anx_engine_tap_info(self._h, k, *[C.byref(x) for x in v]))
+            out[v[0].value] = (k, v[1].value, v[2].value, v[3].value, bool(v[4].value))
+        return out
+
+    def forward_taps(self, x: torch.Tensor, layers, encode_only: bool = False):
+        """``Unet.forward(x, layers, encode_only)`` of the reference (network.py:475-529) for tap
+        indices the engine materialises: ``(output, taps)``, or ``taps`` alone when ``encode_only``
+        stops at ``layers[-1]``.  Taps come back in slot order, fp32 NCDHW."""
+        table = self.tap_table()
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        steps = self.lib.anx_engine_num_steps(self._h)
+        stop_early = encode_only and layers[-1] in table
+        wanted = sorted({i for i in layers if i in table and (not stop_early or i <= layers[-1])})
+        last = table[layers[-1]][3] + 1 if stop_early else steps
+        out = torch.empty((n, self.output_nc, d, h, w), dtype=torch.float32, device=self.device)
+        taps = []
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_run_steps(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, 0, last))
+            for idx in wanted:
+                k, ch, lvl, _, is_output = table[idx]
+                if is_output:
+                    taps.append(out)
+                    continue
+                t = torch.empty((n, ch, d >> lvl, h >> lvl, w >> lvl), dtype=torch.float32, device=self.device)
+                self._check(self.lib.anx_engine_export_tap(
+                    self._h, k, n, d, h, w, ws.data_ptr(), ws.numel(), t.data_ptr(), stream))
+                taps.append(t)
+        return taps if stop_early else (out, taps)
 
     # -- forward ---------------------------------------------------------------
     def workspace_bytes(self, n, d, h, w) -> int:
@@ -238,8 +294,6 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
     it."""
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         return "input is not a CUDA tensor"
-    if len(layers) > 0:
-        return "feature taps requested"
     if x.numel() == 0:
         return "empty batch"
     if cfg["dimension"] != 3 or x.dim() != 5:
@@ -271,6 +325,12 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
         return "spatial size not a multiple of 2^num_downs (the reference fails here too)"
     if x.dtype != torch.float32:
         return "input is not fp32"
+    if len(layers) > 0:
+        # feature taps (network.py:475-529): served when every tapped slot is a tensor the engine stores
+        missing = module._engine_binding().untappable(x.device, layers)
+        if missing:
+            return (f"feature tap at slot {missing[0]} is not materialised by the engine "
+                    "(pre-norm conv outputs are folded into the weights)")
     return None
 
 
@@ -282,23 +342,47 @@ class ModuleBinding:
     def __init__(self, module: nn.Module, cfg: dict):
         self.module = module
         self.cfg = cfg
-        self.engines: Dict[torch.device, Engine] = {}
-        self.stamps: Dict[torch.device, tuple] = {}
+        self.engines: Dict[tuple, Engine] = {}
+        self.stamps: Dict[tuple, tuple] = {}
 
     def _stamp(self):
         return tuple((t.data_ptr(), t._version) for t in
                      list(self.module.parameters()) + list(self.module.buffers()))
 
-    def engine_for(self, device: torch.device) -> Engine:
-        eng = self.engines.get(device)
+    def engine_for(self, device: torch.device, flags: int = 0) -> Engine:
+        key = (device, flags)
+        eng = self.engines.get(key)
         if eng is None:
-            eng = Engine(self.cfg, device)
-            self.engines[device] = eng
+            eng = Engine(self.cfg, device, flags)
+            self.engines[key] = eng
         stamp = self._stamp()
-        if self.stamps.get(device) != stamp:
+        if self.stamps.get(key) != stamp:
             eng.load_state(self.module.state_dict())
-            self.stamps[device] = stamp
+            self.stamps[key] = stamp
         return eng
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.engine_for(x.device).forward(x)
+
+    # -- feature taps ----------------------------------------------------------
+    def _tap_engine(self, device: torch.device, layers):
+        """(engine, missing): the engine variant that stores every tapped slot.  The default program
+        evaluates the upsampled half of the last decoder conv at low resolution and never builds that
+        concat tensor; a tap there uses the single-launch variant (ANX_FLAG_NO_UPCONV)."""
+        valid = [i for i in layers if isinstance(i, int) and 0 <= i < len(self.module.model)]
+        eng, missing = None, valid
+        for flags in (0, _lib.FLAG_NO_UPCONV):
+            eng = self.engine_for(device, flags)
+            table = eng.tap_table()
+            missing = [i for i in valid if i not in table]
+            if not missing:
+                break
+        return eng, missing
+
+    def untappable(self, device: torch.device, layers):
+        return self._tap_engine(device, layers)[1]
+
+    def forward_taps(self, x: torch.Tensor, layers, encode_only: bool):
+        eng, missing = self._tap_engine(x.device, layers)
+        assert not missing, missing
+        return eng.forward_taps(x, list(layers), encode_only)

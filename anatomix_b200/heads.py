@@ -1,0 +1,153 @@
+"""Consumers right behind the U-Net forward.
+
+* Segmentation: the reference finetunes ``nn.Sequential(Unet, UnetOutBlock(3, C, n_classes + 1, False))``
+  (``anatomix/segmentation/segmentation_utils.py:114-115``) and runs it as the sliding-window predictor
+  (``train_segmentation.py:194-199``).  `UnetOutBlock` is MONAI's block (a bias-carrying 1x1x1 conv; MONAI is
+  not importable offline, so it is restated here with the same state-dict keys) and `FusedHeadSequential`
+  is that two-module Sequential whose eligible forwards run on the engine with the head evaluated inside
+  the last conv's epilogue (``anx_engine_set_head``): the 16-channel feature volume never reaches HBM.
+* Registration: ``pred * downscale_feat_scalar`` then ``F.avg_pool3d(pred, grid_sp, stride=grid_sp)``
+  (``anatomix/registration/run_convex_adam_with_network_feats.py:166-167, 198-205``):
+  `scaled_features` folds the scalar into the same epilogue (a diagonal head), `avg_pool3d_scaled` is the
+  streaming pooling kernel behind ``anx_avgpool3d_scale_f32``.
+
+Everything that is not eligible for the engine (training, CPU tensors, autograd) runs the stock torch
+modules, exactly like the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+HEAD_MAX = 32          # csrc/layout.cuh
+
+
+class UnetOutBlock(nn.Module):
+    """``monai.networks.blocks.dynunet_block.UnetOutBlock``: one 1x1(x1) convolution with bias, no norm,
+    no activation; parameters live at ``conv.conv.{weight,bias}`` as in MONAI."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, dropout=None):
+        super().__init__()
+        if dropout not in (None, False, 0, 0.0):
+            raise NotImplementedError("dropout in the output block is not restated (the reference passes False)")
+        conv = getattr(nn, f"Conv{spatial_dims}d")(in_channels, out_channels, kernel_size=1, stride=1, bias=True)
+        self.conv = nn.Sequential(OrderedDict(conv=conv))
+
+    def forward(self, inp):
+        return self.conv(inp)
+
+
+def pointwise_conv_of(head: nn.Module) -> Optional[nn.Conv3d]:
+    """The single 1x1x1 ``nn.Conv3d`` a head consists of, or None when it is anything else."""
+    leaves = [m for m in head.modules() if not list(m.children()) and not isinstance(m, nn.Identity)]
+    if len(leaves) != 1 or not isinstance(leaves[0], nn.Conv3d):
+        return None
+    c = leaves[0]
+    if tuple(c.kernel_size) != (1, 1, 1) or tuple(c.stride) != (1, 1, 1) or c.groups != 1 \
+            or c.padding not in ((0, 0, 0), "same", "valid"):
+        return None
+    return c
+
+
+class FusedHeadSequential(nn.Sequential):
+    """``nn.Sequential(unet, head)`` (same children, same state-dict keys ``0.*`` / ``1.*``) whose eligible
+    forwards run on the engine with the head fused into the last conv."""
+
+    def __init__(self, unet: nn.Module, head: nn.Module):
+        super().__init__(unet, head)
+        self._engines: Dict[torch.device, tuple] = {}
+
+    def fused_ineligible_reason(self, x) -> Optional[str]:
+        unet, head = self[0], self[1]
+        if not hasattr(unet, "engine_ineligible_reason"):
+            return "the first module is not an anatomix_b200 Unet"
+        why = unet.engine_ineligible_reason(x)
+        if why is not None:
+            return why
+        conv = pointwise_conv_of(head)
+        if conv is None:
+            return "the head is not a single 1x1x1 convolution"
+        if conv.out_channels > HEAD_MAX or unet._anx_cfg["output_nc"] > 16 or conv.in_channels != unet._anx_cfg["output_nc"]:
+            return "head / feature widths outside the fused epilogue's range"
+        if torch.is_grad_enabled() and any(p.requires_grad for p in head.parameters()):
+            return "autograd is recording"
+        return None
+
+    def _engine(self, device):
+        from .engine import Engine
+        unet, conv = self[0], pointwise_conv_of(self[1])
+        stamp = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        eng, old = self._engines.get(device, (None, None))
+        if eng is None:
+            eng = Engine(unet._anx_cfg, device)
+        if old != stamp:
+            eng.load_state(unet.state_dict())
+            eng.set_head(conv.weight, conv.bias)
+            self._engines[device] = (eng, stamp)
+        return eng
+
+    def forward(self, x):
+        import os
+        if os.environ.get("ANATOMIX_B200_DISABLE") != "1" and self.fused_ineligible_reason(x) is None:
+            return self._engine(x.device).forward(x)
+        return super().forward(x)
+
+
+def fuse_output_head(unet: nn.Module, head: nn.Module) -> FusedHeadSequential:
+    """Drop-in for ``torch.nn.Sequential(model, fin_layer)`` of segmentation_utils.py:115."""
+    return FusedHeadSequential(unet, head)
+
+
+class _ScaledUnet(nn.Module):
+    def __init__(self, unet: nn.Module, scale: float):
+        super().__init__()
+        self.unet, self.scale = unet, float(scale)
+        self._engines: Dict[torch.device, tuple] = {}
+
+    def forward(self, x):
+        import os
+        unet = self.unet
+        if os.environ.get("ANATOMIX_B200_DISABLE") == "1" or unet.engine_ineligible_reason(x) is not None \
+                or unet._anx_cfg["output_nc"] > 16:
+            return unet(x) * self.scale
+        from .engine import Engine
+        stamp = tuple((t.data_ptr(), t._version) for t in list(unet.parameters()) + list(unet.buffers()))
+        eng, old = self._engines.get(x.device, (None, None))
+        if eng is None:
+            eng = Engine(unet._anx_cfg, x.device)
+        if old != stamp:
+            eng.load_state(unet.state_dict())
+            eng.set_head(torch.eye(unet._anx_cfg["output_nc"]) * self.scale, None)
+            self._engines[x.device] = (eng, stamp)
+        return eng.forward(x)
+
+
+def scaled_features(unet: nn.Module, scale: float) -> nn.Module:
+    """A predictor returning ``unet(x) * scale`` with the multiply folded into the last conv's epilogue
+    (run_convex_adam_with_network_feats.py:166-167: ``downscale_feat_scalar``)."""
+    return _ScaledUnet(unet, scale)
+
+
+def avg_pool3d_scaled(x: torch.Tensor, k: int, scale: float = 1.0) -> torch.Tensor:
+    """``scale * F.avg_pool3d(x, k, stride=k)`` for fp32 ``[N, C, D, H, W]``; CUDA tensors go through the
+    engine library's streaming kernel, anything else through torch."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 5 or (torch.is_grad_enabled() and x.requires_grad) \
+            or min(x.shape[2:]) < k or (k == 2 and x.shape[4] % 2):
+        return F.avg_pool3d(x, k, stride=k) * scale
+    lib = _lib.load()
+    x = x.contiguous()
+    n, c, d, h, w = x.shape
+    out = torch.empty((n, c, d // k, h // k, w // k), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = lib.anx_avgpool3d_scale_f32(x.data_ptr(), out.data_ptr(), n * c, d, h, w, k, C.c_float(scale),
+                                         torch.cuda.current_stream(x.device).cuda_stream)
+    if st != _lib.ANX_OK:
+        raise _lib.EngineError(st, "anx_avgpool3d_scale_f32")
+    return out

@@ -182,8 +182,10 @@ class Unet(nn.Module):
         tensor; with ``layers`` (module indices) returns ``(output, taps)``, or
         only ``taps`` when ``encode_only`` stops at ``layers[-1]``."""
         tapping = len(layers) > 0
-        if os.environ.get("ANATOMIX_B200_DISABLE") != "1" and \
+        if os.environ.get("ANATOMIX_B200_DISABLE") != "1" and not (tapping and verbose) and \
                 self.engine_ineligible_reason(input, layers) is None:
+            if tapping:
+                return self._engine_binding().forward_taps(input, layers, encode_only)
             return self._engine_binding().forward(input)
 
         feat, taps, skips, held = input, [], [], None

@@ -157,6 +157,45 @@ anx_status anx_engine_forward_host(anx_engine *engine, const float *in_host, flo
                                    float *dev_in, float *dev_out,
                                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- rows next to the hot path -------------------------------------------
+ *
+ * Linear head fused into the last conv's epilogue: out[k] = bias[k] + sum_c weight[k][c] * y[c]
+ * for k < head_nc, i.e. a 1x1x1 Conv3d on the network output evaluated on the accumulators
+ * before they leave the SM.  Replaces: `nn.Sequential(Unet, UnetOutBlock(3, C, n_classes + 1))(x)`
+ * (reference anatomix/segmentation/segmentation_utils.py:114-115) and, with a diagonal weight,
+ * `pred * downscale_feat_scalar` (anatomix/registration/run_convex_adam_with_network_feats.py:166-167).
+ * `weight` is fp32 [head_nc][output_nc] (the Conv3d weight with its 1x1x1 tail dropped), `bias`
+ * fp32 [head_nc] or NULL.  Afterwards every forward writes fp32 [N, head_nc, D, H, W]
+ * (anx_engine_out_channels).  head_nc = 0 removes the head.  Needs output_nc <= 16, head_nc <= 32. */
+anx_status anx_engine_set_head(anx_engine *engine, int32_t head_nc, const float *weight,
+                               const float *bias, int32_t location);
+int32_t anx_engine_out_channels(const anx_engine *engine);
+
+/* Feature taps -- `Unet.forward(input, layers=[...], encode_only)` (network.py:475-529).  The engine
+ * can hand out the activation after Sequential slot `module_index` when it stores that tensor:
+ * the last slot of every conv block (its post-norm, post-activation output), the pooling slots,
+ * the Upsample slots (where the reference taps cat(skip, upsampled), network.py:545) and the last
+ * conv (the network output itself).  Pre-norm conv outputs are never materialised (BatchNorm is
+ * folded into the weights): a binding sends such calls down the stock torch path.
+ * `anx_engine_tap_info` lists the available sites; `last_step` is the launch after which the tensor
+ * is complete (run [0, last_step] with anx_engine_run_steps for `encode_only`); `is_output` marks the
+ * last conv, whose tensor is the forward's fp32 output buffer itself;
+ * `anx_engine_export_tap` converts tap `k` to fp32 NCDHW [N, channels, D>>level, H>>level, W>>level]. */
+int32_t anx_engine_num_taps(const anx_engine *engine);
+anx_status anx_engine_tap_info(const anx_engine *engine, int32_t k, int32_t *module_index,
+                               int32_t *channels, int32_t *level, int32_t *last_step,
+                               int32_t *is_output);
+anx_status anx_engine_export_tap(anx_engine *engine, int32_t k, int32_t n, int32_t d, int32_t h,
+                                 int32_t w, void *workspace, size_t workspace_bytes,
+                                 float *out_ncdhw, void *stream);
+
+/* out = scale * avg_pool3d(in, k, stride=k) on a contiguous fp32 [nc, D, H, W] device tensor (floor
+ * mode), on the current device.  Replaces: `pred * downscale_feat_scalar` followed by
+ * `F.avg_pool3d(features, grid_sp, stride=grid_sp)`
+ * (anatomix/registration/run_convex_adam_with_network_feats.py:166-167, 198-205). */
+anx_status anx_avgpool3d_scale_f32(const float *in, float *out, int64_t nc, int32_t d, int32_t h,
+                                   int32_t w, int32_t k, float scale, void *stream);
+
 /* Number of kernel launches one forward of this shape issues (for bench.py's
  * `gpu_launches`); -1 on a bad shape. */
 int32_t anx_engine_launches_per_forward(const anx_engine *engine, int32_t n, int32_t d,

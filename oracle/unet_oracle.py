@@ -138,10 +138,15 @@ def upconv_lowres(low, w_up, shift, rnd):
 
 
 @torch.no_grad()
-def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False, emulate_upconv=True):
+def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False, emulate_upconv=True,
+                 encode_only=False):
     """Forward of ``Unet(**cfg)`` holding ``state`` (a state dict) on input ``x``
     ``[N, input_nc, D, H, W]`` fp32.  Returns the output, or ``(output, taps)``
-    when ``layers`` (module indices) is non-empty (network.py:475-529)."""
+    when ``layers`` (module indices) is non-empty (network.py:475-529); with
+    ``encode_only`` the walk stops at slot ``layers[-1]`` and only the taps come back
+    (network.py:521-526).  The reference's ReLU / LeakyReLU / SELU are in-place modules
+    (network.py:171-204), so a tensor tapped at the slot right before one of them is
+    overwritten by it: such a tap holds the POST-activation values."""
     c = dict(DEFAULTS)
     c.update(cfg)
     assert c["dimension"] == 3 and c["pad_type"] == "reflect"
@@ -153,6 +158,7 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
     sdt = engine_storage_dtype(c)
     _rnd = lambda t: t.to(sdt).to(torch.float32)
     feat, skips, taps = x.to(torch.float32), [], []
+    tap_slot = {}                                    # module index -> position in `taps`
     eps = c["norm_eps"]
     n_conv = 0
     # the engine runs the conv behind the LAST nearest upsample as low-resolution + skip halves
@@ -180,6 +186,7 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
                     if c["use_skip_connection"] and idx in enc_idx:
                         skips.append(feat)
                     if idx in layers:
+                        tap_slot[idx] = len(taps)
                         taps.append(feat.clone())
                     continue
                 if n_conv > 0:                       # stem conv stays fp32
@@ -213,6 +220,8 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
             feat = _activate(feat, c["activation"])
             if engine_rounding:
                 feat = _rnd(feat)                    # activations live in HBM in the storage type
+            if (idx - 1) in tap_slot and c["activation"] in ("relu", "lrelu", "selu"):
+                taps[tap_slot[idx - 1]] = feat.clone()   # in-place activation overwrote the tapped tensor
         elif op == "final_act":
             feat = _activate(feat, c["final_act"])
         elif op == "pool":                           # network.py:297,368
@@ -234,7 +243,10 @@ def unet_forward(cfg, state, x, layers=(), training=False, engine_rounding=False
             if idx in enc_idx:
                 skips.append(feat)
         if idx in layers:
+            tap_slot[idx] = len(taps)
             taps.append(feat.clone())
+            if encode_only and idx == layers[-1]:
+                return taps
     return (feat, taps) if len(layers) else feat
 
 

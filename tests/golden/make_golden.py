@@ -55,6 +55,36 @@ def structured_inputs(S=32):
     return out
 
 
+def write_manifest():
+    with open(os.path.join(HERE, "MANIFEST.txt"), "w") as f:
+        f.write("minted by tests/golden/make_golden.py from /root/reference (torch %s)\n" % torch.__version__)
+        for name in sorted(os.listdir(HERE)):
+            if name.endswith(".npz"):
+                h = hashlib.sha256(open(os.path.join(HERE, name), "rb").read()).hexdigest()[:16]
+                f.write(f"{name} {os.path.getsize(os.path.join(HERE, name))} {h}\n")
+    print(open(os.path.join(HERE, "MANIFEST.txt")).read())
+
+
+def mint_g7(Unet, sd):
+    """G7: the feature-tap branch (network.py:475-529) at slots the engine serves -- norm slots (which hold
+    POST-activation values: the in-place ReLU overwrites the tapped tensor), activation, pooling and
+    Upsample (concat) slots, the last conv -- plus an `encode_only` call."""
+    m6 = Unet(**CFG_6M); m6.load_state_dict(sd, strict=True); m6.eval()
+    ids = [1, 2, 9, 16, 30, 36, 37, 44, 51, 58, 60, 61, 64, 65]
+    enc = [8, 22, 15]                      # stops at slot layers[-1] = 15: taps of 8 and 15 only
+    with torch.no_grad():
+        x = rand_input((1, 1, 32, 32, 32), 3)
+        y, taps = m6(x, layers=ids)
+        g = {"tap_ids": np.array(ids), "out_s2": sub(y, 2), "enc_ids": np.array(enc)}
+        for i, t in zip(ids, taps):
+            g[f"tap{i}"] = sub(t, 2) if t.shape[-1] > 4 else t.numpy()
+        only = m6(x, layers=enc, encode_only=True)
+        g["enc_count"] = np.array(len(only))
+        for k, t in enumerate(only):
+            g[f"enc{k}"] = sub(t, 2)
+    np.savez_compressed(os.path.join(HERE, "g7_6m_taps.npz"), **g)
+
+
 def main():
     sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.abspath(os.path.join(HERE, "..", ".."))]
     sys.path.insert(0, REF)
@@ -62,6 +92,10 @@ def main():
     import anatomix.model.network as net
     assert net.__file__.startswith(REF), net.__file__
     torch.set_num_threads(os.cpu_count())
+    if sys.argv[1:] == ["g7"]:             # add G7 without re-minting the others
+        mint_g7(Unet, torch.load(os.path.join(REF, "model-weights", "anatomix.pth"), map_location="cpu"))
+        write_manifest()
+        return
 
     sd = torch.load(os.path.join(REF, "model-weights", "anatomix.pth"), map_location="cpu")
     np.savez_compressed(os.path.join(HERE, "anatomix_6m_state.npz"),
@@ -119,13 +153,8 @@ def main():
         g[f"tap{i}_mom"] = moments(t)
     np.savez_compressed(os.path.join(HERE, "g4_94m_64.npz"), **g)
 
-    with open(os.path.join(HERE, "MANIFEST.txt"), "w") as f:
-        f.write("minted by tests/golden/make_golden.py from /root/reference (torch %s)\n" % torch.__version__)
-        for name in sorted(os.listdir(HERE)):
-            if name.endswith(".npz"):
-                h = hashlib.sha256(open(os.path.join(HERE, name), "rb").read()).hexdigest()[:16]
-                f.write(f"{name} {os.path.getsize(os.path.join(HERE, name))} {h}\n")
-    print(open(os.path.join(HERE, "MANIFEST.txt")).read())
+    mint_g7(Unet, sd)
+    write_manifest()
 
 
 if __name__ == "__main__":

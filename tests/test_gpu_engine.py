@@ -275,13 +275,13 @@ def test_module_routes_to_engine_and_back(state_6m):
         assert m.engine_ineligible_reason(xc) is None
         y = m(xc)
         check_against_oracle(CFG_6M, state_6m, x, y)
-        y_taps, taps = m(xc, layers=[8])          # tap path stays on torch
+        y_taps, taps = m(xc, layers=[8])          # a stored tensor: served by the engine too
         assert rel_l2(y.cpu(), y_taps.cpu()) <= LOOSE_REL
         # finetuning mutates parameters in place: the packed weights must follow
         m.model[65].weight.mul_(2.0)
         y2 = m(xc)
     assert rel_l2(y2.cpu(), 2 * y.cpu()) < 1e-2
-    assert list(m._anx_binding.engines) == [torch.device("cuda", 0)]
+    assert list(m._anx_binding.engines) == [(torch.device("cuda", 0), 0)]
 
 
 @pytest.mark.parametrize("input_nc", [2, 3, 4])
@@ -395,3 +395,107 @@ def test_errors_mirror_the_reference(state_6m):
     assert "NOT_READY" in str(ei.value)
     with pytest.raises(EngineError):
         Engine(dict(CFG_6M, ngf=24), "cuda:0")   # widths the tensor-core tiles cannot take
+
+
+# ------------------------------------------------------------------ rows next to the hot path
+def test_feature_taps_on_the_engine_g7(state_6m):
+    """`forward(x, layers=[...])` (network.py:475-529) served from the tensors the engine stores: against
+    golden G7 minted from the reference (loose gate: 16-bit storage) and the 16-bit-emulating oracle."""
+    from anatomix_b200 import Unet
+    g = golden("g7_6m_taps.npz")
+    ids = [int(i) for i in g["tap_ids"]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    x = rand_input((1, 1, 32, 32, 32), 3)
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(x.cuda(), ids) is None
+        y, taps = m(x.cuda(), layers=ids)
+        assert "not materialised" in m.engine_ineligible_reason(x.cuda(), [8, 59])     # pre-norm conv output
+        y_t, taps_t = m(x.cuda(), layers=[8, 59])                                      # ... stock torch path
+    torch.cuda.synchronize()
+    assert len(taps) == len(ids) and taps[-1] is y                       # slot 65 is the output itself
+    _, emu = O.unet_forward(CFG_6M, state_6m, x, layers=ids, engine_rounding=True)
+    for i, t, e in zip(ids, taps, emu):
+        got = t.float().cpu()
+        want = torch.from_numpy(g[f"tap{i}"])
+        sub = got[:, :, ::2, ::2, ::2] if got.shape[-1] > 4 else got
+        assert sub.shape == want.shape, (i, sub.shape, want.shape)
+        r = rel_l2(sub, want)
+        assert r <= LOOSE_REL, f"tap {i}: rel-L2 {r:.3e} vs reference golden"
+        rt = rel_l2(got, e)
+        assert rt <= TIGHT_REL, f"tap {i}: rel-L2 {rt:.3e} vs 16-bit-emulating oracle"
+    assert rel_l2(y_t.cpu(), y.cpu()) <= LOOSE_REL and len(taps_t) == 2
+    # encode_only stops at layers[-1] (= 15 here) and returns the taps alone
+    enc = [int(i) for i in g["enc_ids"]]
+    with torch.no_grad():
+        only = m(x.cuda(), layers=enc, encode_only=True)
+    assert isinstance(only, list) and len(only) == int(g["enc_count"])
+    for k, t in enumerate(only):
+        r = rel_l2(t.float().cpu()[:, :, ::2, ::2, ::2], torch.from_numpy(g[f"enc{k}"]))
+        assert r <= LOOSE_REL, f"encode_only tap {k}: {r:.3e}"
+
+
+def test_feature_taps_instance_norm_network():
+    cfg = small_cfg(norm="instance", pooling="Avg", interp="trilinear", norm_eps=1e-2, num_downs=2)
+    state = O.random_state(cfg, seed=4)
+    x = rand_input((2, 1, 16, 16, 8), 6)
+    eng = make_engine(cfg, state)
+    table = eng.tap_table()
+    ids = sorted(table)
+    y, taps = eng.forward_taps(x.cuda(), ids)
+    torch.cuda.synchronize()
+    _, emu = O.unet_forward(cfg, state, x, layers=ids, engine_rounding=True)
+    for i, t, e in zip(ids, taps, emu):
+        assert t.shape == e.shape, (i, t.shape, e.shape)
+        r = rel_l2(t.float().cpu(), e)
+        assert r <= 2e-2, f"tap {i}: rel-L2 {r:.3e}"
+
+
+def test_fused_output_head_matches_pointwise_conv(state_6m):
+    """nn.Sequential(Unet, UnetOutBlock) (segmentation_utils.py:114-115) with the 1x1x1 conv evaluated in the
+    last conv's epilogue: identical (fp32 rounding) to applying the conv to the engine's own features."""
+    import torch.nn.functional as F
+    from anatomix_b200 import Unet
+    from anatomix_b200.heads import UnetOutBlock, fuse_output_head, scaled_features
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    torch.manual_seed(3)
+    head = UnetOutBlock(3, 16, 5, False)
+    seq = fuse_output_head(m, head).cuda().eval()
+    assert list(seq.state_dict())[-2:] == ["1.conv.conv.weight", "1.conv.conv.bias"]
+    x = rand_input((2, 1, 32, 48, 32), 8)
+    with torch.no_grad():
+        assert seq.fused_ineligible_reason(x.cuda()) is None
+        got = seq(x.cuda())
+        feats = m(x.cuda())
+        # fp64 on the CPU (cuDNN would use TF32 for this conv)
+        want = F.conv3d(feats.cpu().double(), head.conv.conv.weight.cpu().double(), head.conv.conv.bias.cpu().double())
+        assert got.shape == (2, 5, 32, 48, 32)
+        assert rel_l2(got.cpu(), want.cpu()) < 1e-5
+        # against the fp32 oracle end to end
+        ref = F.conv3d(O.unet_forward(CFG_6M, state_6m, x), head.conv.conv.weight.cpu(), head.conv.conv.bias.cpu())
+        assert rel_l2(got.cpu(), ref) <= LOOSE_REL
+        # finetuning the head in place is picked up
+        head.conv.conv.bias.add_(1.0)
+        assert rel_l2(seq(x.cuda()).cpu(), (want + 1.0).cpu()) < 1e-5
+        # registration: pred * downscale_feat_scalar folded into the epilogue (a diagonal head)
+        scaled = scaled_features(m, 0.1)(x.cuda())
+        assert rel_l2(scaled.cpu(), (feats * 0.1).cpu()) < 1e-6
+    seq.train()
+    with torch.no_grad():
+        assert seq.fused_ineligible_reason(x.cuda()) is not None      # BatchNorm batch statistics: stock torch
+
+
+@pytest.mark.parametrize("k,shape", [(2, (1, 16, 32, 32, 32)), (3, (2, 5, 20, 17, 31)), (4, (1, 3, 16, 24, 36))])
+def test_scaled_average_pooling_kernel(k, shape):
+    """scale * F.avg_pool3d(x, k, stride=k) (run_convex_adam_with_network_feats.py:166-167, 198-205)."""
+    import torch.nn.functional as F
+    from anatomix_b200.heads import avg_pool3d_scaled
+    x = rand_input(shape, 21).cuda()
+    got = avg_pool3d_scaled(x, k, 0.1)
+    want = F.avg_pool3d(x, k, stride=k) * 0.1
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)

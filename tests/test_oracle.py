@@ -85,6 +85,25 @@ def test_g6_structured_inputs(state_6m):
         np.testing.assert_allclose(sub(y, 2), g[name], atol=TOL, rtol=1e-4, err_msg=name)
 
 
+def test_g7_feature_taps_and_encode_only(state_6m):
+    """Tap branch (network.py:475-529): norm-slot taps hold post-activation values (in-place ReLU),
+    Upsample-slot taps the concat, `encode_only` stops at layers[-1]."""
+    g = golden("g7_6m_taps.npz")
+    ids = [int(i) for i in g["tap_ids"]]
+    x = rand_input((1, 1, 32, 32, 32), 3)
+    y, taps = O.unet_forward(CFG_6M, state_6m, x, layers=ids)
+    np.testing.assert_allclose(sub(y, 2), g["out_s2"], atol=TOL, rtol=1e-4)
+    assert len(taps) == len(ids)
+    for i, t in zip(ids, taps):
+        got = sub(t, 2) if t.shape[-1] > 4 else t.numpy()
+        np.testing.assert_allclose(got, g[f"tap{i}"], atol=TOL, rtol=1e-4, err_msg=f"tap {i}")
+    assert taps[0].min() >= 0 and torch.equal(taps[0], taps[1])          # slot 1 (BatchNorm) aliases slot 2 (ReLU)
+    only = O.unet_forward(CFG_6M, state_6m, x, layers=[int(i) for i in g["enc_ids"]], encode_only=True)
+    assert isinstance(only, list) and len(only) == int(g["enc_count"]) == 2
+    for k, t in enumerate(only):
+        np.testing.assert_allclose(sub(t, 2), g[f"enc{k}"], atol=TOL, rtol=1e-4, err_msg=f"encode_only tap {k}")
+
+
 def test_c_restatement_matches_golden_g1(state_6m):
     g = golden("g1_6m_32.npz")
     y = unet_forward_c(CFG_6M, state_6m, rand_input((1, 1, 32, 32, 32), 0).numpy())
