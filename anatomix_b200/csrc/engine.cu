@@ -1233,13 +1233,28 @@ anx_status anx_engine_export_tap(anx_engine *e, int32_t k, int32_t n, int32_t d,
 anx_status anx_avgpool3d_scale_f32(const float *in, float *out, int64_t nc, int32_t d, int32_t h, int32_t w,
                                    int32_t k, float scale, void *stream) {
     if (!in || !out || nc < 1 || k < 1 || d < k || h < k || w < k) return ANX_ERR_BAD_ARG;
-    if (k == 2 && ((w & 1) || (reinterpret_cast<uintptr_t>(in) & 7))) return ANX_ERR_BAD_ARG;   // float2 loads
     const size_t items = (size_t)nc * (d / k) * (h / k) * (w / k);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess) return ANX_ERR_NO_DEVICE;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    avgpool3d_scale_kernel<<<grid_for(items, 256, sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        in, out, (size_t)nc, d, h, w, k, scale);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (k == 2 && w % 4 == 0 && !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 7))
+        avgpool3d_scale_k2_kernel<<<grid_for(items / 2, 256, sms, 32), 256, 0, st>>>(in, out, (size_t)nc, d, h, w, scale);
+    else
+        avgpool3d_scale_kernel<<<grid_for(items, 256, sms, 32), 256, 0, st>>>(in, out, (size_t)nc, d, h, w, k, scale);
+    return cudaGetLastError() == cudaSuccess ? ANX_OK : ANX_ERR_CUDA;
+}
+
+anx_status anx_blend_window_f32(const float *pred, const float *weight, float *out, float *norm, int32_t channels,
+                                int32_t d, int32_t h, int32_t w, int32_t D, int32_t H, int32_t W, int32_t z0,
+                                int32_t y0, int32_t x0, void *stream) {
+    if (!pred || !weight || !out || !norm || channels < 1 || d < 1 || h < 1 || w < 1) return ANX_ERR_BAD_ARG;
+    if (z0 < 0 || y0 < 0 || x0 < 0 || z0 + d > D || y0 + h > H || x0 + w > W) return ANX_ERR_BAD_SHAPE;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    blend_window_kernel<<<grid_for((size_t)d * h * w, 256, sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pred, weight, out, norm, channels, d, h, w, D, H, W, z0, y0, x0);
     return cudaGetLastError() == cudaSuccess ? ANX_OK : ANX_ERR_CUDA;
 }
 

@@ -293,14 +293,59 @@ avgpool3d_scale_kernel(const float *__restrict__ in, float *__restrict__ out, si
         for (int dz = 0; dz < k; ++dz)
             for (int dy = 0; dy < k; ++dy) {
                 const float *row = src + ((size_t)dz * H + dy) * W;
-                if (k == 2) {
-                    const float2 p = __ldg(reinterpret_cast<const float2 *>(row));   // x*k even, W even when k == 2 divides it
-                    a += p.x + p.y;
-                } else {
-                    for (int dx = 0; dx < k; ++dx) a += __ldg(row + dx);
-                }
+                for (int dx = 0; dx < k; ++dx) a += __ldg(row + dx);
             }
         out[id] = a * norm;
+    }
+}
+
+// k = 2, W a multiple of 4, 16-byte aligned input: one thread per PAIR of output voxels, 128-bit loads
+// (a warp reads four 512-byte runs and writes 256 contiguous bytes).
+__global__ void __launch_bounds__(256)
+avgpool3d_scale_k2_kernel(const float *__restrict__ in, float *__restrict__ out, size_t NC, int D, int H, int W,
+                          float scale) {
+    const int Do = D / 2, Ho = H / 2, Wq = W / 4;
+    const size_t total = NC * Do * Ho * Wq;
+    const float norm = scale * 0.125f;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+        size_t v = id;
+        const int xq = (int)(v % Wq); v /= Wq;
+        const int y = (int)(v % Ho); v /= Ho;
+        const int z = (int)(v % Do);
+        const size_t nc = v / Do;
+        const float *src = in + ((nc * D + (size_t)z * 2) * H + (size_t)y * 2) * W + (size_t)xq * 4;
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const float4 p = __ldg(reinterpret_cast<const float4 *>(src + ((size_t)dz * H + dy) * W));
+                a += p.x + p.y;
+                b += p.z + p.w;
+            }
+        *reinterpret_cast<float2 *>(out + ((nc * Do + z) * Ho + y) * (size_t)(W / 2) + (size_t)xq * 2) =
+            make_float2(a * norm, b * norm);
+    }
+}
+
+// ------------------------------------------------------- sliding-window blend
+// One window of a sliding-window scan (MONAI-style inferer, reference convex_adam_utils.py:202-219):
+//   out[c, z0+z, y0+y, x0+x] += pred[c, z, y, x] * weight[z, y, x]      norm[z0+z, y0+y, x0+x] += weight[z, y, x]
+// One thread per window voxel, lanes along x, all channels in a loop (the weight is read once).  Windows of
+// one scan overlap, so the caller launches them one after another on one stream.
+__global__ void __launch_bounds__(256)
+blend_window_kernel(const float *__restrict__ pred, const float *__restrict__ weight, float *__restrict__ out,
+                    float *__restrict__ norm, int C, int d, int h, int w, int D, int H, int W, int z0, int y0, int x0) {
+    const size_t wvol = (size_t)d * h * w, vol = (size_t)D * H * W;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < wvol; id += (size_t)gridDim.x * blockDim.x) {
+        size_t v = id;
+        const int x = (int)(v % w); v /= w;
+        const int y = (int)(v % h);
+        const int z = (int)(v / h);
+        const float g = __ldg(weight + id);
+        const size_t o = ((size_t)(z0 + z) * H + (y0 + y)) * W + (x0 + x);
+        norm[o] += g;
+        for (int c = 0; c < C; ++c) out[(size_t)c * vol + o] = fmaf(__ldg(pred + (size_t)c * wvol + id), g, out[(size_t)c * vol + o]);
     }
 }
 

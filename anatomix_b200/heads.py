@@ -139,7 +139,7 @@ def avg_pool3d_scaled(x: torch.Tensor, k: int, scale: float = 1.0) -> torch.Tens
     """``scale * F.avg_pool3d(x, k, stride=k)`` for fp32 ``[N, C, D, H, W]``; CUDA tensors go through the
     engine library's streaming kernel, anything else through torch."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 5 or (torch.is_grad_enabled() and x.requires_grad) \
-            or min(x.shape[2:]) < k or (k == 2 and x.shape[4] % 2):
+            or min(x.shape[2:]) < k:
         return F.avg_pool3d(x, k, stride=k) * scale
     lib = _lib.load()
     x = x.contiguous()

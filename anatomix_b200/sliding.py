@@ -23,6 +23,21 @@ import torch
 import torch.nn.functional as F
 
 
+_LIB = None
+
+
+def _lib_or_none():
+    """The engine library for the native blend kernel (CUDA tensors only; torch ops otherwise)."""
+    global _LIB
+    if _LIB is None:
+        try:
+            from . import _lib
+            _LIB = _lib.load()
+        except Exception:
+            _LIB = False
+    return _LIB or None
+
+
 def scan_intervals(image_size: Sequence[int], roi_size: Sequence[int], overlap: float) -> List[int]:
     """Per-axis stride between windows: the whole axis when the window covers it,
     else ``int(roi * (1 - overlap))`` (at least 1)."""
@@ -97,7 +112,19 @@ def sliding_window_features(inputs: torch.Tensor, roi_size: Sequence[int], sw_ba
         pred = predictor(patch.contiguous())
         if out is None:
             out = torch.zeros((batch, pred.shape[1]) + size, dtype=torch.float32, device=x.device)
+        native = pred.is_cuda and pred.dtype == torch.float32 and _lib_or_none() is not None
+        if native:
+            pred = pred.contiguous()
+            stream = torch.cuda.current_stream(pred.device).cuda_stream
         for k, (b, z, y, w) in enumerate(group):
+            if native:      # one streaming pass per window: weight read once, no temporaries
+                with torch.cuda.device(pred.device):
+                    st = _LIB.anx_blend_window_f32(pred[k].data_ptr(), weight.data_ptr(), out[b].data_ptr(),
+                                                   norm[b].data_ptr(), pred.shape[1], roi[0], roi[1], roi[2],
+                                                   size[0], size[1], size[2], z, y, w, stream)
+                if st != 0:
+                    raise RuntimeError(f"anx_blend_window_f32 failed with status {st}")
+                continue
             out[b, :, z:z + roi[0], y:y + roi[1], w:w + roi[2]] += pred[k] * weight
             norm[b, :, z:z + roi[0], y:y + roi[1], w:w + roi[2]] += weight
     out /= norm

@@ -196,6 +196,16 @@ anx_status anx_engine_export_tap(anx_engine *engine, int32_t k, int32_t n, int32
 anx_status anx_avgpool3d_scale_f32(const float *in, float *out, int64_t nc, int32_t d, int32_t h,
                                    int32_t w, int32_t k, float scale, void *stream);
 
+/* One window of a sliding-window scan: out[c, z0+z, y0+y, x0+x] += pred[c, z, y, x] * weight[z, y, x] and
+ * norm[z0+z, ...] += weight[z, y, x], for fp32 device tensors pred [channels, d, h, w], weight [d, h, w],
+ * out [channels, D, H, W], norm [D, H, W].  Replaces the accumulate step of MONAI's
+ * `sliding_window_inference` as the reference calls it (anatomix/registration/convex_adam_utils.py:202-219,
+ * anatomix/segmentation/train_segmentation.py:194-199).  Windows of one scan overlap: launch them one
+ * after another on one stream. */
+anx_status anx_blend_window_f32(const float *pred, const float *weight, float *out, float *norm,
+                                int32_t channels, int32_t d, int32_t h, int32_t w, int32_t D, int32_t H,
+                                int32_t W, int32_t z0, int32_t y0, int32_t x0, void *stream);
+
 /* Number of kernel launches one forward of this shape issues (for bench.py's
  * `gpu_launches`); -1 on a bad shape. */
 int32_t anx_engine_launches_per_forward(const anx_engine *engine, int32_t n, int32_t d,

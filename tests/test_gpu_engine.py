@@ -499,3 +499,15 @@ def test_scaled_average_pooling_kernel(k, shape):
     want = F.avg_pool3d(x, k, stride=k) * 0.1
     assert got.shape == want.shape
     assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)
+
+
+def test_native_blend_kernel_matches_torch_accumulate():
+    """anx_blend_window_f32 (the accumulate step of the sliding-window inferer) against the same window
+    grid accumulated with torch ops on the CPU; ragged volume, overlapping windows, gaussian weights."""
+    from anatomix_b200.sliding import sliding_window_features
+    pred = lambda p: torch.cat([p * 1.0, p * p, 1.0 - p], dim=1)
+    x = rand_input((2, 1, 40, 37, 52), 17)
+    want = sliding_window_features(x, (16, 16, 24), 4, pred, overlap=0.6, mode="gaussian", sigma_scale=0.25)
+    got = sliding_window_features(x.cuda(), (16, 16, 24), 4, pred, overlap=0.6, mode="gaussian", sigma_scale=0.25)
+    assert got.shape == want.shape == (2, 3, 40, 37, 52)
+    assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
