@@ -591,12 +591,14 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             g.ncols = c.ncols;
             g.kq = (9 * c.cin + 15) / 16;
             g.bz = std::min(std::max(1, std::min(8, 256 / c.ncols)), p.D);
+            if (c.ncols == 16 && c.cin == 1 && p.D >= 16 && !getenv("ANX_NO_BZ16")) g.bz = 16;   // all of TMEM: 18 input planes per 16
             g.acc_stages = 2;
             int cols = 32;
             while (cols < g.acc_stages * g.bz * g.ncols) cols *= 2;
             g.tmem_cols = cols;
             g.z_halo = zh0;
             if (const char *ds = getenv("ANX_STEM_SHIFT")) g.dbg_shift = atoi(ds);
+            if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
             g.tiles_x = (p.W + TILE_X - 1) / TILE_X;
             g.tiles_y = (p.H + TILE_Y - 1) / TILE_Y;
             g.tiles_z = (p.D + g.bz - 1) / g.bz;
@@ -605,7 +607,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             g.brick_bytes = (uint32_t)(c.cin * (g.bz + 2) * HALO_Y * STEM_BRICK_X * 4);
             g.a_tile_bytes = (uint32_t)(g.kq * 2 * 128 * 16);
             g.b_bytes = (uint32_t)(g.kq * 2 * 3 * g.ncols * 16);
-            g.smem_bytes = 2 * ((g.brick_bytes + 127) & ~127u) + STEM_A_SLOTS * 2 * g.a_tile_bytes + 2 * g.b_bytes +
+            g.smem_bytes = stem_bricks(g.kq) * ((g.brick_bytes + 127) & ~127u) + stem_a_slots(g.kq) * 2 * g.a_tile_bytes + 2 * g.b_bytes +
                            (uint32_t)sizeof(StemShared);
             if (g.smem_bytes > (uint32_t)e->max_smem)
                 return e->fail(ANX_ERR_UNSUPPORTED, "stem tile does not fit shared memory (%u bytes)", g.smem_bytes);

@@ -16,20 +16,33 @@
 // padding of network.py:310-318 is applied by re-indexing inside the brick) and
 // write the canonical K-major non-swizzled core matrices.
 //
-// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
 // issuer, warps 2..9 = epilogue (same code path as the generic conv: shift-seeded
-// accumulators, reflect-shell stores, instance-norm statistics), warps 10..13 =
-// A-tile builders (thread = voxel of the 8x16 patch).
+// accumulators, reflect-shell stores, instance-norm statistics), warps 10..17 =
+// A-tile builders: two groups of 128 threads (thread = voxel of the 8x16 patch) that
+// take alternate input planes -- the build (shared-memory reads, hi/lo split, stores,
+// proxy fence) is a latency chain per plane, and one group alone left the MMA issuer
+// and the epilogue waiting (ncu: 23 % of all samples in the epilogue's accumulator wait).
 #pragma once
 #include "conv_umma.cuh"
 
 namespace anx {
 
-constexpr int STEM_THREADS = 64 + 32 * EPI_WARPS + 128;
+constexpr int STEM_BUILD_GROUPS = 2;      // builder groups of 128 threads (thread = voxel); group g builds planes ka = g (mod groups)
+constexpr int STEM_THREADS = 64 + 32 * EPI_WARPS + 128 * STEM_BUILD_GROUPS;
 constexpr int STEM_BRICK_X = 16;          // x0-4 .. x0+11: TMA wants the innermost start 16-byte aligned
 constexpr int STEM_X_LEAD = 4;            // brick index of coordinate x0
 constexpr int STEM_MAX_KQ = 3;            // K chunks of 16: 9*Cin <= 48  (Cin <= 4 uses 36)
-constexpr int STEM_A_SLOTS = 4;           // A-tile ring (one slot = one input plane, hi + lo)
+constexpr int STEM_MAX_A_SLOTS = 8;
+// A-tile ring (one slot = one input plane, hi + lo).  The builder -> MMA -> builder hand-over is a
+// round trip of mbarrier latencies, so the ring depth bounds the planes in flight: 8 slots of 8 KB for
+// the single-channel stem, 4 (of 16 / 24 KB) when the K chunks are larger.
+__host__ __device__ constexpr int stem_a_slots(int kq) { return kq == 1 ? 8 : 4; }
+// Halo bricks in flight (fp32 TMA boxes of 64-byte rows straight from the network input in HBM): the
+// load of brick k + depth is issued when brick k is released, so depth - 1 tiles of build time must
+// cover the box latency.
+constexpr int STEM_MAX_BRICKS = 4;
+__host__ __device__ constexpr int stem_bricks(int kq) { return kq == 1 ? 4 : 2; }
 
 struct StemGeom {
     int N, D, H, W, cin;
@@ -42,11 +55,12 @@ struct StemGeom {
     uint32_t b_bytes;                     // kq * 2 * (3*ncols) * 16 (one of hi / lo)
     uint32_t smem_bytes;
     int dbg_shift;                        // experiments only
+    uint32_t ablate;                      // timing experiments (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A build, 8 no brick load
 };
 
 struct StemShared {
-    uint64_t full_brick[2], empty_brick[2];
-    uint64_t full_a[STEM_A_SLOTS], empty_a[STEM_A_SLOTS];
+    uint64_t full_brick[STEM_MAX_BRICKS], empty_brick[STEM_MAX_BRICKS];
+    uint64_t full_a[STEM_MAX_A_SLOTS], empty_a[STEM_MAX_A_SLOTS];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_slot;
     uint32_t pad[3];
@@ -69,10 +83,12 @@ __global__ void __launch_bounds__(STEM_THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, const uint8_t *__restrict__ wpack,
                  const Epilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int STEM_A_SLOTS = stem_a_slots(KQ);
+    constexpr uint32_t NB = stem_bricks(KQ);
     // [brick 0][brick 1][A slots: hi, lo][B hi][B lo][StemShared]
     const uint32_t brick_stride = (g.brick_bytes + 127) & ~127u;
     uint8_t *bricks = smem;
-    uint8_t *a_ring = bricks + 2 * brick_stride;
+    uint8_t *a_ring = bricks + NB * brick_stride;
     uint8_t *b_hi = a_ring + (size_t)STEM_A_SLOTS * 2 * g.a_tile_bytes;
     uint8_t *b_lo = b_hi + g.b_bytes;
     StemShared *sh = reinterpret_cast<StemShared *>(b_lo + g.b_bytes);
@@ -83,9 +99,11 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
     const int planes = g.bz + 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (uint32_t i = 0; i < NB; ++i) {
             mbar_init(&sh->full_brick[i], 1);
-            mbar_init(&sh->empty_brick[i], 128);
+            mbar_init(&sh->empty_brick[i], 128 * STEM_BUILD_GROUPS);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&sh->tmem_full[i], 1);
             mbar_init(&sh->tmem_empty[i], 32 * EPI_WARPS);
         }
@@ -116,8 +134,9 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 const int tz = r / (g.tiles_y * g.tiles_x);
                 r -= tz * g.tiles_y * g.tiles_x;
                 const int ty = r / g.tiles_x, tx = r - ty * g.tiles_x;
-                const uint32_t s = k & 1;
-                mbar_wait(&sh->empty_brick[s], ((k >> 1) & 1) ^ 1, 11);
+                const uint32_t s = k % NB;
+                mbar_wait(&sh->empty_brick[s], ((k / NB) & 1) ^ 1, 11);
+                if (g.ablate & 8) { mbar_arrive(&sh->full_brick[s]); continue; }
                 mbar_arrive_expect_tx(&sh->full_brick[s], g.brick_bytes);
                 // box {16 x, 18 y, bz+2 z, cin}; planes of (n, c) are consecutive along dim 3
                 tma_load_4d(bricks + s * brick_stride, &tmap_in, &sh->full_brick[s], tx * TILE_X - STEM_X_LEAD + g.dbg_shift,
@@ -152,19 +171,27 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 const uint32_t al = ah + (g.a_tile_bytes >> 4);
 #pragma unroll
                 for (int kc = 0; kc < KQ; ++kc) {
+                    if (g.ablate & 1) break;
                     const uint32_t ao = kc * (2 * 128), bo = kc * (2 * R) + row0;   // 16 B units per K chunk of 16
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (ah + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (al + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (ah + ao) | a_lbo), make_desc(a_hi_bits, (bl + bo) | b_lbo), idesc);
                 }
-                umma_commit_warp(&sh->empty_a[sa]);
+                if (g.ablate & 16) {          // timing experiment (no MMAs in flight): plain arrive instead of tcgen05.commit
+                    if (lane == 0) mbar_arrive(&sh->empty_a[sa]);
+                    __syncwarp();
+                } else {
+                    umma_commit_warp(&sh->empty_a[sa]);
+                }
             }
             umma_commit_warp(&sh->tmem_full[s]);
         }
         __syncwarp();
     } else if (warp >= 2 + EPI_WARPS) {
         // ------------------------------------------------------- A-tile builders
-        const int r = threadIdx.x - (64 + 32 * EPI_WARPS);   // voxel of the 8 x 16 patch
+        const int bt = threadIdx.x - (64 + 32 * EPI_WARPS);
+        const uint32_t group = (uint32_t)bt >> 7;            // alternate input planes between the builder groups
+        const int r = bt & 127;                               // voxel of the 8 x 16 patch
         const int ly = r >> 3, lx = r & 7;
         uint32_t k = 0, ka = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++k) {
@@ -186,11 +213,17 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 bx[t] = brick_reflect(min(lx + t + STEM_X_LEAD - 1, xhi + 1), xlo, xhi);
                 by[t] = brick_reflect(min(ly + t, yhi + 1), ylo, yhi);
             }
-            const uint32_t s = k & 1;
-            mbar_wait(&sh->full_brick[s], (k >> 1) & 1, 15);
+            const uint32_t s = k % NB;
+            mbar_wait(&sh->full_brick[s], (k / NB) & 1, 15);
             const float *brick = reinterpret_cast<const float *>(bricks + s * brick_stride);
             for (int j = 0; j < planes; ++j, ++ka) {
+                if (ka % STEM_BUILD_GROUPS != group) continue;
                 const uint32_t sa = ka % STEM_A_SLOTS;
+                if (g.ablate & 4) {
+                    mbar_wait(&sh->empty_a[sa], ((ka / STEM_A_SLOTS) & 1) ^ 1, 16);
+                    mbar_arrive(&sh->full_a[sa]);
+                    continue;
+                }
                 const int bzj = brick_reflect(min(j, zhi + 1), zlo, zhi);
                 // K index = c*9 + (dy*3+dx); 16*KQ slots, unused ones are zero
                 float v[16 * KQ];
@@ -252,7 +285,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             et.n = n; et.z0 = tz * g.bz; et.y = ty * TILE_Y + ly; et.x = tx * TILE_X + lx;
             et.chan0 = 0;
             et.in_xy = (et.y < g.H) && (et.x < g.W);
-            et.store = true;
+            et.store = !(g.ablate & 2);
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
             umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);
