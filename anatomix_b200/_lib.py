@@ -9,7 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libanatomix_b200.so")
+_VARIANT = os.environ.get("ANX_LIB_VARIANT", "")      # experiments only, see build.py
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                        "libanatomix_b200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 ANX_OK = 0
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "BAD_SHAPE", 3: "UNSUPPORTED", 4: "WORKSPACE",

@@ -15,8 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "lib", "obj")
-LIB = os.path.join(PKG, "lib", "libanatomix_b200.so")
+# experiments: ANX_LIB_VARIANT=<tag> builds lib/libanatomix_b200_<tag>.so with the extra nvcc flags in
+# ANX_BUILD_DEFS (e.g. -DANX_EPI_WARPS=16); _lib.py loads the same variant when the variable is set
+VARIANT = os.environ.get("ANX_LIB_VARIANT", "")
+OBJ = os.path.join(PKG, "lib", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(PKG, "lib", "libanatomix_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 SOURCES = ["engine.cu", "selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -51,7 +54,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *os.environ.get("ANX_BUILD_DEFS", "").split(), "-c", src, "-o", obj],
+                           capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return src, r.stderr

@@ -35,7 +35,11 @@
 
 namespace anx {
 
-constexpr int EPI_WARPS = 8;
+#ifndef ANX_EPI_WARPS
+#define ANX_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = ANX_EPI_WARPS;     // generic conv kernel: multiple of 4 (one or more warps per TMEM lane quadrant)
+constexpr int STEM_EPI_WARPS = 8;
 constexpr int UMMA_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
@@ -224,7 +228,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
     } else {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;                    // TMEM lane quadrant this warp may touch
-        const int half = (warp - 2) >> 2;          // which of the quadrant's two warps: takes planes b = half (mod 2)
+        const PlaneSplit half{(warp - 2) >> 2, EPI_WARPS / 4, MODE == EPI_POOL};   // this warp's run of output planes
         const int r = q * 32 + lane;               // accumulator row = voxel within the 8x16 patch
         const int ly = r >> 3, lx = r & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -29,7 +29,7 @@
 namespace anx {
 
 constexpr int STEM_BUILD_GROUPS = 2;      // builder groups of 128 threads (thread = voxel); group g builds planes ka = g (mod groups)
-constexpr int STEM_THREADS = 64 + 32 * EPI_WARPS + 128 * STEM_BUILD_GROUPS;
+constexpr int STEM_THREADS = 64 + 32 * STEM_EPI_WARPS + 128 * STEM_BUILD_GROUPS;
 constexpr int STEM_BRICK_X = 16;          // x0-4 .. x0+11: TMA wants the innermost start 16-byte aligned
 constexpr int STEM_X_LEAD = 4;            // brick index of coordinate x0
 constexpr int STEM_MAX_KQ = 3;            // K chunks of 16: 9*Cin <= 48  (Cin <= 4 uses 36)
@@ -105,7 +105,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sh->tmem_full[i], 1);
-            mbar_init(&sh->tmem_empty[i], 32 * EPI_WARPS);
+            mbar_init(&sh->tmem_empty[i], 32 * STEM_EPI_WARPS);
         }
         for (int i = 0; i < STEM_A_SLOTS; ++i) { mbar_init(&sh->full_a[i], 128); mbar_init(&sh->empty_a[i], 1); }
         fence_barrier_init();
@@ -187,9 +187,9 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             umma_commit_warp(&sh->tmem_full[s]);
         }
         __syncwarp();
-    } else if (warp >= 2 + EPI_WARPS) {
+    } else if (warp >= 2 + STEM_EPI_WARPS) {
         // ------------------------------------------------------- A-tile builders
-        const int bt = threadIdx.x - (64 + 32 * EPI_WARPS);
+        const int bt = threadIdx.x - (64 + 32 * STEM_EPI_WARPS);
         const uint32_t group = (uint32_t)bt >> 7;            // alternate input planes between the builder groups
         const int r = bt & 127;                               // voxel of the 8 x 16 patch
         const int ly = r >> 3, lx = r & 7;
@@ -261,7 +261,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
     } else {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const PlaneSplit half{(warp - 2) >> 2, STEM_EPI_WARPS / 4, 0};
         const int r = q * 32 + lane;
         const int ly = r >> 3, lx = r & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);

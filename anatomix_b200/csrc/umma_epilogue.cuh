@@ -18,10 +18,15 @@ struct EpiTile {
     bool store;             // false only in timing experiments
 };
 
-// Planes of a tile are split between the two warps of a TMEM lane quadrant in contiguous
-// halves: warp `half` owns [plane_lo, plane_hi).
-__device__ __forceinline__ int plane_lo(int half, int bz) { return half * ((bz + 1) >> 1); }
-__device__ __forceinline__ int plane_hi(int half, int bz) { return half ? bz : ((bz + 1) >> 1); }
+// Planes of a tile are split between the `parts` warps of a TMEM lane quadrant in contiguous runs:
+// warp `part` owns [plane_lo, plane_hi).  `pairs`: runs of even length (the fused pooling reduces z pairs).
+struct PlaneSplit { int part, parts, pairs; };
+__device__ __forceinline__ int plane_run(int bz, const PlaneSplit &ps) {
+    const int per = (bz + ps.parts - 1) / ps.parts;
+    return ps.pairs ? (per + 1) & ~1 : per;
+}
+__device__ __forceinline__ int plane_lo(const PlaneSplit &ps, int bz) { return min(bz, ps.part * plane_run(bz, ps)); }
+__device__ __forceinline__ int plane_hi(const PlaneSplit &ps, int bz) { return min(bz, plane_lo(ps, bz) + plane_run(bz, ps)); }
 
 // Seeded accumulators (ncols = 16: two 8-channel groups per plane): the partial sums of the tile that
 // will reuse an accumulator stage are pulled towards L1 while the warp waits for the MMAs, and loaded
@@ -32,7 +37,7 @@ __device__ __forceinline__ const uint4 *seed_ptr(const Epilogue &ep, const EpiTi
 __device__ __forceinline__ bool seed_valid(const EpiTile &t, bool tile_valid, int b, int D) {
     return tile_valid && t.in_xy && (t.z0 + b) < D;
 }
-__device__ __forceinline__ void prefetch_seeds(const Epilogue &ep, const EpiTile &t, bool tile_valid, int half, int bz,
+__device__ __forceinline__ void prefetch_seeds(const Epilogue &ep, const EpiTile &t, bool tile_valid, const PlaneSplit &half, int bz,
                                                int D) {
     for (int b = plane_lo(half, bz); b < plane_hi(half, bz); ++b)
         if (seed_valid(t, tile_valid, b, D)) {
@@ -65,7 +70,7 @@ constexpr int HEAD_SMEM_OFFSET = 32;   // floats behind the channel shift in sha
 // `next` / `next_valid`: the tile that will reuse this accumulator stage (seeded kernels only).
 template <int MODE>
 __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
-                                                   const float *seed, int half, int bz, int ncols, int D,
+                                                   const float *seed, const PlaneSplit &half, int bz, int ncols, int D,
                                                    const EpiTile &next, bool next_valid) {
     const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
     const size_t plane = (size_t)(Hh + 2) * ep.dst.pitch;      // uint4 units
