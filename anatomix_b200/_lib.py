@@ -35,7 +35,7 @@ EXPORTS = [
     "anx_engine_last_error", "anx_version", "anx_selftest",
     "anx_engine_num_steps", "anx_engine_step_info", "anx_engine_run_steps",
     "anx_engine_forward_allgather", "anx_engine_row_layout", "anx_engine_set_head", "anx_engine_out_channels",
-    "anx_engine_num_taps", "anx_engine_tap_info", "anx_engine_export_tap", "anx_avgpool3d_scale_f32", "anx_blend_window_f32",
+    "anx_engine_num_taps", "anx_engine_tap_info", "anx_engine_export_tap", "anx_avgpool3d_scale_f32", "anx_blend_window_f32", "anx_engine_set_slab", "anx_engine_step_stats",
 ]
 
 
@@ -118,6 +118,10 @@ def load():
     lib.anx_avgpool3d_scale_f32.restype = i32
     lib.anx_blend_window_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
     lib.anx_blend_window_f32.restype = i32
+    lib.anx_engine_set_slab.argtypes = [vp, i32, i32, i32]
+    lib.anx_engine_set_slab.restype = i32
+    lib.anx_engine_step_stats.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    lib.anx_engine_step_stats.restype = i32
     lib.anx_status_string.argtypes = [i32]
     lib.anx_status_string.restype = C.c_char_p
     lib.anx_engine_last_error.argtypes = [vp]

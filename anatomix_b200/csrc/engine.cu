@@ -158,6 +158,9 @@ struct anx_engine {
     std::vector<Step> steps;
     std::vector<TapSite> taps;
     // optional linear head fused into the last conv's epilogue (anx_engine_set_head)
+    // depth-slab mode (anx_engine_set_slab): which z faces of this slab have a neighbour, and the depth of the
+    // whole volume (instance-norm statistics are per whole volume)
+    int slab_lower = 0, slab_upper = 0, slab_depth_total = 0;
     int head_nc = 0;
     float *d_head = nullptr;          // [HEAD_MAX][16] weights then [HEAD_MAX] bias
     std::mutex mu;
@@ -689,15 +692,17 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         if (e->desc.interp_kind == ANX_INTERP_NEAREST)
             upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
         else
-            upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
-                                                                                   e->desc.interp_kind, e->dt);
+            upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(
+                src, dst, p.N, s.groups, e->desc.interp_kind, e->dt, e->slab_lower, e->slab_upper);
         break;
     }
     case STEP_NORM: {
         const ConvLayer &c = e->convs[s.conv];
         ActView t = view_of(e, p, s.dst_buf, s.dst_group_offset);
         const size_t count = (size_t)(t.D + 2) * (t.H + 2) * (t.W + 2);
-        const double inv = 1.0 / ((double)t.D * t.H * t.W);
+        // statistics are over the whole volume: in depth-slab mode the caller has all-reduced the sums
+        const int depth = e->slab_depth_total > 0 ? e->slab_depth_total >> e->bufs[s.dst_buf].level : t.D;
+        const double inv = 1.0 / ((double)depth * t.H * t.W);
         const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>(1024, (count + 2047) / 2048));
         const double *stats = reinterpret_cast<const double *>(static_cast<char *>(p.workspace) + p.conv_stats_offset[s.conv]);
         inorm_act_kernel<<<dim3(gx, (unsigned)(p.N * s.groups)), 256, 0, st>>>(
@@ -1162,6 +1167,32 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
     }
     ANX_CUDA(e, cudaEventRecord(e->ev_join, e->d2h_stream));
     ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));   // the caller's stream completes after the last download
+    return ANX_OK;
+}
+
+anx_status anx_engine_set_slab(anx_engine *e, int32_t has_lower, int32_t has_upper, int32_t depth_total) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (depth_total < 0 || (depth_total % (1 << e->desc.num_downs)) != 0)
+        return e->fail(ANX_ERR_BAD_ARG, "total depth %d is not a multiple of %d", depth_total, 1 << e->desc.num_downs);
+    e->slab_lower = has_lower ? 1 : 0;
+    e->slab_upper = has_upper ? 1 : 0;
+    e->slab_depth_total = depth_total;
+    return ANX_OK;
+}
+
+anx_status anx_engine_step_stats(const anx_engine *e, int32_t step, int32_t n, int32_t d, int32_t h, int32_t w,
+                                 size_t *offset, size_t *bytes) {
+    if (!e || step < 0 || step >= (int)e->steps.size() || !shape_ok(e, n, d, h, w)) return ANX_ERR_BAD_ARG;
+    const Step &s = e->steps[step];
+    if (offset) *offset = 0;
+    if (bytes) *bytes = 0;
+    if ((s.kind != STEP_STEM && s.kind != STEP_CONV) || !e->convs[s.conv].inorm) return ANX_OK;
+    size_t off = 0;
+    for (auto &b : e->bufs) off += buffer_bytes(e, b, n, d, h, w);
+    for (int i = 0; i < s.conv; ++i)
+        if (e->convs[i].inorm) off += align_up((size_t)n * e->convs[i].ncols * 2 * sizeof(double), 256);
+    if (offset) *offset = off;
+    if (bytes) *bytes = (size_t)n * e->convs[s.conv].ncols * 2 * sizeof(double);
     return ANX_OK;
 }
 

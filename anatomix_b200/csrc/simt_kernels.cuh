@@ -208,8 +208,19 @@ upsample2_nearest_kernel(ActView src, ActView dst, int N, int groups) {
     }
 }
 
+// z axis of a depth slab (one oversized volume split over several GPUs): at an interior slab face the
+// interpolation reads the neighbour's boundary plane from the shell (index -1 / n) instead of clamping.
+__device__ __forceinline__ void tri_src_slab(int o, int n, bool lo_open, bool hi_open, int &i0, int &i1, float &t) {
+    float s = (o + 0.5f) * 0.5f - 0.5f;
+    if (!lo_open) s = fmaxf(s, 0.0f);
+    i0 = (int)floorf(s);
+    t = s - (float)i0;
+    i1 = i0 + 1;
+    if (i1 > n - 1 && !hi_open) i1 = n - 1;
+}
+
 __global__ void __launch_bounds__(256)
-upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt) {
+upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt, int z_lo_open, int z_hi_open) {
     const size_t total = (size_t)N * groups * dst.D * dst.H * dst.W;
     for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
         size_t v = id;
@@ -224,7 +235,7 @@ upsample2_kernel(ActView src, ActView dst, int N, int groups, int kind, int dt) 
         } else {
             int z0, z1, y0, y1, x0, x1;
             float tz, ty, tx;
-            tri_src(z, src.D, z0, z1, tz);
+            tri_src_slab(z, src.D, z_lo_open != 0, z_hi_open != 0, z0, z1, tz);
             tri_src(y, src.H, y0, y1, ty);
             tri_src(x, src.W, x0, x1, tx);
             float o[8];

@@ -277,6 +277,16 @@ class Engine:
         self._check(self.lib.anx_engine_row_layout(self._h, w, C.byref(lead), C.byref(pitch)))
         return lead.value, pitch.value
 
+    def set_slab(self, has_lower: bool, has_upper: bool, depth_total: int):
+        """Depth-slab mode (anx_engine_set_slab): neighbours at the z faces, depth of the whole volume."""
+        self._check(self.lib.anx_engine_set_slab(self._h, int(has_lower), int(has_upper), depth_total))
+
+    def step_stats(self, step: int, n, d, h, w):
+        """(offset, bytes) of the InstanceNorm sums the given step accumulates (bytes == 0: none)."""
+        off, nb = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.anx_engine_step_stats(self._h, step, n, d, h, w, C.byref(off), C.byref(nb)))
+        return off.value, nb.value
+
     def buffer_table(self, n, d, h, w):
         """[(offset, bytes, level, groups)] of the workspace's activation buffers."""
         out = []

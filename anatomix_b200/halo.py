@@ -13,9 +13,13 @@ runs unchanged; reflect padding survives only at the two global faces.  The
 network input is handed over with the neighbour planes attached
 (ANX_FLAG_DEPTH_HALO_INPUT).
 
-Supported: BatchNorm-eval / no-norm networks with nearest upsampling (the released
-6M model).  InstanceNorm would additionally need an all-reduce of the per-layer
-statistics, trilinear upsampling a low-resolution halo read.
+InstanceNorm networks (`anatomix-dev`): the statistics are per whole volume, so the
+sums every conv accumulates (doubles, from its fp32 accumulators) are all-reduced
+over the slabs before the normalisation step runs (`anx_engine_step_stats`), and the
+normalisation divides by the whole volume's voxel count (`anx_engine_set_slab`).
+Trilinear upsampling reads the neighbour's boundary plane from the shell at interior
+slab faces.  Average / max pooling and nearest upsampling are slab-local because the
+boundaries are multiples of ``2**num_downs``.
 """
 from __future__ import annotations
 
@@ -44,8 +48,9 @@ class DepthSlabExtractor:
     ``gather=True``."""
 
     def __init__(self, cfg: dict, state: dict, device, group: Optional[dist.ProcessGroup] = None):
-        if cfg.get("norm", "batch") not in ("batch", "none") or cfg.get("interp", "nearest") != "nearest":
-            raise NotImplementedError("depth-slab mode covers BatchNorm-eval / nearest-upsampling networks")
+        if cfg.get("norm", "batch") not in ("batch", "none", "instance") \
+                or cfg.get("interp", "nearest") not in ("nearest", "trilinear"):
+            raise NotImplementedError("depth-slab mode covers batch / instance / no norm with nearest / trilinear upsampling")
         self.cfg = cfg
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -72,13 +77,22 @@ class DepthSlabExtractor:
         n, _, depth, h, w = volume.shape
         z_lo, z_hi = slab_bounds(depth, self.world, self.cfg["num_downs"])[self.rank]
         d = z_hi - z_lo
+        self.engine.set_slab(self.rank > 0, self.rank < self.world - 1, depth if self.world > 1 else 0)
         x = slab_input_with_halo(volume, z_lo, z_hi).to(self.engine.device, torch.float32)
         out = torch.empty((n, self.cfg["output_nc"], d, h, w), dtype=torch.float32, device=self.engine.device)
         ws = self.engine.workspace(n, d, h, w)
         table = self.engine.buffer_table(n, d, h, w)
         for i, (kind, buf, goff, groups, name) in enumerate(self.steps):
             self.engine.run_steps(x, out, i, i + 1)
-            if buf >= 0 and self.world > 1:
+            if self.world == 1:
+                continue
+            off, nbytes = self.engine.step_stats(i, n, d, h, w)
+            if nbytes:
+                # InstanceNorm: whole-volume statistics before the normalisation step that follows; the raw
+                # planes need no exchange, the normalised ones are swapped after that step
+                dist.all_reduce(ws[off:off + nbytes].view(torch.float64), group=self.group)
+                continue
+            if buf >= 0:
                 self._exchange(ws, table, buf, goff, groups, n, d, h, w)
         if not gather or self.world == 1:
             return out

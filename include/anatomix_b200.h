@@ -136,6 +136,19 @@ anx_status anx_engine_run_steps(anx_engine *engine, const float *in_ncdhw, float
                                 void *workspace, size_t workspace_bytes, void *stream,
                                 int32_t first_step, int32_t last_step);
 
+/* Depth-slab mode for networks with InstanceNorm and / or trilinear upsampling (`anatomix-dev`):
+ * `anx_engine_set_slab` tells the engine which z faces of its slab touch a neighbouring slab (the
+ * trilinear upsample then reads the neighbour's boundary plane from the shell instead of clamping) and
+ * the depth of the WHOLE volume (InstanceNorm statistics are per whole volume: mean / variance are taken
+ * over depth_total x H x W).  Every conv that feeds an InstanceNorm accumulates its sums into a block of
+ * doubles [n][cout rounded up to 16][sum, sum of squares] inside the workspace; `anx_engine_step_stats`
+ * gives that block for a step (bytes = 0 for any other step), and the caller all-reduces it over the
+ * slabs between that step and the normalisation step that follows.  depth_total = 0 switches the mode off. */
+anx_status anx_engine_set_slab(anx_engine *engine, int32_t has_lower_neighbour,
+                               int32_t has_upper_neighbour, int32_t depth_total);
+anx_status anx_engine_step_stats(const anx_engine *engine, int32_t step, int32_t n, int32_t d,
+                                 int32_t h, int32_t w, size_t *offset, size_t *bytes);
+
 /* Batch-sharded forward fused with the feature all-gather: the last conv's epilogue
  * stores this rank's `n` output volumes straight into EVERY rank's gather buffer
  * (`out_peers[r]` = NVLink-mapped device pointer to rank r's fp32

@@ -65,6 +65,24 @@ def _worker(rank, world, port, out_dir):
         with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
             f.write(f"{err} {rel}\n")
         assert rel < 1e-3, f"depth-slab result differs from single-GPU: max abs {err}, rel-L2 {rel}"
+
+        # (3) the same partition for an InstanceNorm / AvgPool / trilinear network (`anatomix-dev` style):
+        # whole-volume statistics via an all-reduce of the per-conv sums, neighbour planes in the upsample
+        from oracle import unet_oracle as O
+        cfg_in = dict(dimension=3, input_nc=1, output_nc=16, num_downs=2, ngf=16, norm="instance",
+                      pooling="Avg", interp="trilinear", norm_eps=1e-2)
+        st_in = O.random_state(cfg_in, seed=9)
+        vol = torch.rand(1, 1, 32, 16, 24, generator=torch.Generator().manual_seed(5))
+        single = Engine(cfg_in, dev)
+        single.load_state(st_in)
+        want = single.forward(vol.to(dev))
+        got = DepthSlabExtractor(cfg_in, st_in, dev).extract(vol, gather=True)
+        torch.cuda.synchronize()
+        rel = ((got - want).norm() / want.norm()).item()
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "a") as f:
+            f.write(f"instance-norm slab: rel-L2 {rel}\n")
+        # not bit-exact: the statistics are summed in a different order, which can flip a 16-bit rounding
+        assert rel < 5e-3, f"InstanceNorm depth-slab result differs from single-GPU: rel-L2 {rel}"
     finally:
         dist.destroy_process_group()
 
