@@ -1,0 +1,283 @@
+// 16 -> 16 channel 3x3x3 convolution at full-row granularity: the thin layers of the network (reference
+// network.py:334-369, 413-461 at level 0), whose generic tile (M = 8 x 16 voxels, N = 3 * 16 with dz folded) is
+// bound by the tensor core's shared-memory operand fetch -- 4 KB of A feed only 48 columns.
+//
+// Here the 128 TMEM lanes are 128 consecutive x voxels of ONE row, and the accumulator columns enumerate
+// output ROWS: column block (yo * 3 + (z mod 3)) * 16 of a strip of 4 output rows.  One input row (y', z'),
+// shifted by dx, then contributes to up to 3 x 3 output rows that are CONTIGUOUS in TMEM, so a single MMA
+// with N = 144 (B = the 3 x 3 (dy, dz) weight blocks stacked along N) replaces nine N = 16 products: dy AND dz
+// are folded into N, only dx remains as separate instructions.  Shared-memory wavefronts per output row of
+// 128 voxels drop from 9 * 43.5 to about 250.
+//
+// A CTA owns a block of 8 output rows (two strips of 4, alternating so that the epilogue of one overlaps the
+// MMAs of the other) of one 128-wide x tile and streams ZS output planes through a ring of input planes:
+//   producer warp : per input plane, 10 rows x 2 channel groups of 130 voxels -> 20 bulk copies (rows are
+//                   contiguous in the padded planar buffer; no tensor map needed)
+//   MMA warp      : per plane and strip 6 input rows x 3 dx = 18 MMAs (N = 48 / 96 / 144 at the strip edges),
+//                   weights resident in shared memory as three images (rotation of the z slots by z mod 3)
+//   8 epilogue warps: after plane p, output plane p - 2 of the strip is complete: tcgen05.ld, re-seed with
+//                   the channel shift, activation, 16-bit pack, 512-byte contiguous row stores (+ shell mirrors),
+//                   or fp32 NCDHW / fused-head stores for the last conv.
+// Output planes outside the z segment ("phantoms": contributions of the first / last two input planes) are
+// simply re-seeded, so every plane runs the same instruction sequence.
+#pragma once
+#include <cstddef>
+#include "conv_umma.cuh"
+
+namespace anx {
+
+constexpr int ROWS_X = 128;                     // x voxels per tile = TMEM lanes
+constexpr int ROWS_BY = 4;                      // output rows per strip
+constexpr int ROWS_YB = 2 * ROWS_BY;            // output rows per CTA unit
+constexpr int ROWS_IN_Y = ROWS_YB + 2;          // input rows per plane
+constexpr int ROWS_ROW_BYTES = (ROWS_X + 2) * 16;               // one input row of one channel group
+constexpr int ROWS_GROUP_BYTES = ROWS_IN_Y * ROWS_ROW_BYTES;    // LBO: distance between the two K halves
+constexpr int ROWS_PLANE_BYTES = 2 * ROWS_GROUP_BYTES;          // one ring stage
+constexpr int ROWS_STAGES = 4;
+constexpr int ROWS_N = 9 * 16;                  // rows of one B tap matrix
+constexpr int ROWS_B_TAP_BYTES = 2 * ROWS_N * 16;
+constexpr int ROWS_B_IMAGE_BYTES = 3 * ROWS_B_TAP_BYTES;        // three dx taps
+constexpr int ROWS_STRIP_COLS = ROWS_BY * 48;   // TMEM columns of one strip
+constexpr int ROWS_THREADS = 64 + 32 * 8;
+
+struct RowsGeom {
+    int N, D, H, W;
+    int zs;                  // output planes per unit
+    int tiles_x, tiles_y, tiles_z, units_per_sample, total_units;
+    int dt;
+    uint32_t smem_bytes;
+    uint32_t ablate;
+};
+
+struct RowsShared {
+    uint64_t full_a[ROWS_STAGES], empty_a[ROWS_STAGES];
+    uint64_t full_b;
+    uint64_t acc_ready[2], drained[2];
+    uint32_t tmem_slot;
+    uint32_t pad[5];         // keeps `shift` 16-byte aligned (float4 reads of the head weights)
+    float shift[16 + HEAD_FLOATS + 16];
+};
+static_assert(offsetof(RowsShared, shift) % 16 == 0, "shift must be 16-byte aligned");
+
+template <int MODE>   // EPI_PADDED, EPI_F32 or EPI_F32_HEAD
+__global__ void __launch_bounds__(ROWS_THREADS, 1)
+conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *a_ring = smem;
+    uint8_t *b_img = a_ring + (size_t)ROWS_STAGES * ROWS_PLANE_BYTES;
+    RowsShared *sh = reinterpret_cast<RowsShared *>(b_img + 3 * ROWS_B_IMAGE_BYTES);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int planes = g.zs + 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], 1); mbar_init(&sh->empty_a[i], 1); }
+        mbar_init(&sh->full_b, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_ready[i], 1); mbar_init(&sh->drained[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_dyn(&sh->tmem_slot, 512u);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) sh->shift[i] = ep.bias[i];
+    if constexpr (MODE == EPI_F32_HEAD)
+        for (int i = threadIdx.x; i < HEAD_FLOATS; i += blockDim.x) sh->shift[HEAD_SMEM_OFFSET + i] = ep.head[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_slot;
+
+    auto decode = [&](int unit, int &n, int &x0, int &y0, int &z0) {
+        n = unit / g.units_per_sample;
+        int r = unit - n * g.units_per_sample;
+        const int tz = r / (g.tiles_y * g.tiles_x);
+        r -= tz * g.tiles_y * g.tiles_x;
+        const int ty = r / g.tiles_x;
+        x0 = (r - ty * g.tiles_x) * ROWS_X;
+        y0 = ty * ROWS_YB;
+        z0 = tz * g.zs;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0 && blockIdx.x < g.total_units) {
+            mbar_arrive_expect_tx(&sh->full_b, 3 * ROWS_B_IMAGE_BYTES);
+            bulk_load_1d(b_img, wrows, 3 * ROWS_B_IMAGE_BYTES, &sh->full_b);
+        }
+        uint32_t ka = 0;
+        for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+            int n, x0, y0, z0;
+            decode(unit, n, x0, y0, z0);
+            for (int p = 0; p < planes; ++p, ++ka) {
+                const uint32_t st = ka % ROWS_STAGES;
+                if (lane == 0) {
+                    mbar_wait(&sh->empty_a[st], ((ka / ROWS_STAGES) & 1) ^ 1, 21);
+                    if (g.ablate & 4) mbar_arrive(&sh->full_a[st]);
+                    else mbar_arrive_expect_tx(&sh->full_a[st], ROWS_PLANE_BYTES);
+                }
+                __syncwarp();
+                if (!(g.ablate & 4) && lane < 2 * ROWS_IN_Y) {
+                    const int grp = lane / ROWS_IN_Y, row = lane - grp * ROWS_IN_Y;
+                    // padded coordinates: plane z0 + p, row y0 + row, 130 voxels from x0 (= interior x0 - 1)
+                    bulk_load_1d(a_ring + (size_t)st * ROWS_PLANE_BYTES + (size_t)grp * ROWS_GROUP_BYTES +
+                                     (size_t)row * ROWS_ROW_BYTES,
+                                 src.at(n, grp, z0 + p, y0 + row, x0), ROWS_ROW_BYTES, &sh->full_a[st]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------------------------------------- MMA issuer (warp-uniform)
+        uint32_t ka = 0;
+        const uint32_t hi_bits = (128u >> 4) | (1u << 14);                   // SBO = 128 B for A and B
+        const uint32_t a_lbo = ((uint32_t)(ROWS_GROUP_BYTES >> 4) & 0x3FFF) << 16;
+        const uint32_t b_lbo = ((uint32_t)ROWS_N & 0x3FFF) << 16;            // 16 * 144 bytes between the K halves
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t b0 = (smem_u32(b_img) & 0x3FFFF) >> 4;
+        mbar_wait_warp(&sh->full_b, 0, 22);
+        for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+            for (int p = 0; p < planes; ++p, ++ka) {
+                const uint32_t st = ka % ROWS_STAGES;
+                mbar_wait_warp(&sh->full_a[st], (ka / ROWS_STAGES) & 1, 23);
+                const uint32_t a0 = (smem_u32(a_ring + (size_t)st * ROWS_PLANE_BYTES) & 0x3FFFF) >> 4;
+                const uint32_t bimg = b0 + (uint32_t)(p % 3) * (ROWS_B_IMAGE_BYTES >> 4);
+                for (int s = 0; s < 2; ++s) {
+                    mbar_wait_warp(&sh->drained[s], ka & 1, 24);   // the slot this plane touches first is re-seeded
+                    tc_fence_after();
+                    if (!(g.ablate & 1)) {
+#pragma unroll
+                        for (int i = 0; i < ROWS_BY + 2; ++i) {
+                            const int yo_min = i - 2 > 0 ? i - 2 : 0;
+                            const int yo_max = i < ROWS_BY - 1 ? i : ROWS_BY - 1;
+                            const uint32_t nrows = (uint32_t)(yo_max - yo_min + 1);
+                            const uint32_t idesc = idesc_m128(nrows * 48u, g.dt);
+                            const uint32_t dcol = tmem_u + (uint32_t)s * ROWS_STRIP_COLS + (uint32_t)yo_min * 48u;
+                            const uint32_t arow = a0 + (uint32_t)(s * ROWS_BY + i) * (ROWS_ROW_BYTES >> 4);
+                            const uint32_t brow = bimg + (uint32_t)(2 - (i - yo_min)) * 48u;   // 16 B per B row
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+                                umma_bf16_warp(dcol, make_desc(hi_bits, (arow + dx) | a_lbo),
+                                               make_desc(hi_bits, (brow + dx * (ROWS_B_TAP_BYTES >> 4)) | b_lbo), idesc);
+                        }
+                    }
+                    umma_commit_warp(&sh->acc_ready[s]);
+                }
+                umma_commit_warp(&sh->empty_a[st]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int q = warp & 3;                    // TMEM lane quadrant
+        const int h = (warp - 2) >> 2;             // rows {2h, 2h + 1} of each strip
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int lx = q * 32 + lane;
+        const int Dd = g.D, Hh = g.H, Ww = g.W;
+        const size_t vol = (size_t)Dd * Hh * Ww;
+        float sd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sd[i] = sh->shift[i];
+        // every accumulator column starts from the channel shift
+        for (int s = 0; s < 2; ++s) {
+            for (int r = 0; r < 2; ++r)
+                for (int slot = 0; slot < 3; ++slot)
+                    tmem_st16(lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + slot) * 16, sd);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&sh->drained[0]); mbar_arrive(&sh->drained[1]); }
+
+        uint32_t ka = 0;
+        for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+            int n, x0, y0, z0;
+            decode(unit, n, x0, y0, z0);
+            const int x = x0 + lx;
+            for (int p = 0; p < planes; ++p, ++ka) {
+                const int o = p - 2;                               // output plane completed by input plane p
+                const int slot = (o + 3) % 3;
+                const int z = z0 + o;
+                for (int s = 0; s < 2; ++s) {
+                    mbar_wait(&sh->acc_ready[s], ka & 1, 25);
+                    tc_fence_after();
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int yo = 2 * h + r;
+                        const uint32_t col = lane_base + s * ROWS_STRIP_COLS + (yo * 3 + slot) * 16;
+                        __syncwarp();
+                        if (o < 0) {                               // phantom plane below the segment: discard
+                            tmem_st16(col, sd);
+                            continue;
+                        }
+                        uint32_t rr[16];
+                        tmem_ld16_nowait(col, rr);
+                        tmem_wait_ld();
+                        tmem_ld_ready16(rr);
+                        tmem_st16(col, sd);
+                        if (g.ablate & 2) continue;
+                        const int y = y0 + s * ROWS_BY + yo;
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = activate(__uint_as_float(rr[i]), ep.act, ep.slope);
+                        if constexpr (MODE == EPI_PADDED) {
+                            const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
+                            const size_t rowp = (size_t)ep.dst.pitch, plane = rowp * (Hh + 2), gstride = plane * (Dd + 2);
+                            uint4 *pd = ep.dst.at(n, 0, z + 1, y + 1, x + 1);
+                            *pd = q0;
+                            pd[gstride] = q1;
+                            const int rep = ep.dst.shell_rep;
+                            const int mdx = mirror_delta(x, Ww, rep), mdy = mirror_delta(y, Hh, rep),
+                                      mdz = mirror_delta(z, Dd, rep);
+                            if (mdx | mdy | mdz) {
+                                store_mirrors(pd, q0, mdz, mdy, mdx, rowp, plane);
+                                store_mirrors(pd + gstride, q1, mdz, mdy, mdx, rowp, plane);
+                            }
+                        } else if constexpr (MODE == EPI_F32) {
+                            float *po = ep.out_f32 + (size_t)n * ep.cout * vol + ((size_t)z * Hh + y) * Ww + x;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < ep.cout) po[(size_t)i * vol] = v[i];
+                        } else {
+                            const float *hb = sh->shift + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
+                            float *po = ep.out_f32 + (size_t)n * ep.head_nc * vol + ((size_t)z * Hh + y) * Ww + x;
+#pragma unroll 2
+                            for (int k = 0; k < ep.head_nc; ++k) {
+                                float a = hb[k];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 w4 = reinterpret_cast<const float4 *>(hw + k * 16)[i];
+                                    a = fmaf(w4.x, v[4 * i], a);
+                                    a = fmaf(w4.y, v[4 * i + 1], a);
+                                    a = fmaf(w4.z, v[4 * i + 2], a);
+                                    a = fmaf(w4.w, v[4 * i + 3], a);
+                                }
+                                po[(size_t)k * vol] = a;
+                            }
+                        }
+                    }
+                    if (p == planes - 1) {          // phantom planes above the segment: back to the shift
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int e = 1; e <= 2; ++e) {
+                                __syncwarp();
+                                tmem_st16(lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + (slot + e) % 3) * 16, sd);
+                            }
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh->drained[s]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+}   // namespace anx

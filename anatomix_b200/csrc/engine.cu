@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/anatomix_b200.h"
+#include "conv_rows.cuh"
 #include "conv_umma.cuh"
 #include "simt_kernels.cuh"
 #include "stem_umma.cuh"
@@ -93,6 +94,7 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     size_t stats_index = 0;                   // first double of this conv's [N][ncols][2] block, per sample-channel
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
+    void *d_wrows = nullptr;  // 16 -> 16 row kernel: three B images [z rotation][dx][k half][144 rows][8] (conv_rows.cuh)
     float *d_bias = nullptr;  // [ncols]
     size_t wpack_bytes = 0;
 };
@@ -149,6 +151,7 @@ struct ShapePlan {            // everything that depends on (N, D, H, W, workspa
 struct anx_engine {
     anx_unet_desc desc;
     int dt = DT_BF16;         // storage type of activations / packed weights
+    int use_rows = 1;         // thin 16 -> 16 layers run on conv3_rows_kernel when the shape allows (ANX_ROWS=0: never)
     int x_lead = 0;           // row layout of the padded planar buffers (layout.cuh layout_of; ANX_X_LEAD)
     int num_sms = 148;
     int max_smem = 0;
@@ -655,6 +658,26 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
         if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0))
             return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path without a fused gather");
+        if (!force_simt && e->use_rows && c.d_wrows && !g.fuse_pool && !ep.seed_on && !ep.stats && !ep.d2s_cout &&
+            ep.n_peers == 0 && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
+            RowsGeom rg{};
+            rg.N = g.N; rg.D = g.D; rg.H = g.H; rg.W = g.W;
+            rg.zs = 16;
+            rg.tiles_x = g.W / ROWS_X; rg.tiles_y = g.H / ROWS_YB; rg.tiles_z = g.D / rg.zs;
+            rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
+            rg.total_units = rg.units_per_sample * g.N;
+            rg.dt = e->dt;
+            rg.ablate = g.ablate;
+            rg.smem_bytes = (uint32_t)(ROWS_STAGES * ROWS_PLANE_BYTES + 3 * ROWS_B_IMAGE_BYTES + sizeof(RowsShared));
+            const ActView src = view_of(e, p, c.src_buf, 0);
+            const int grid = std::min(rg.total_units, e->num_sms);
+            const uint8_t *wr = (const uint8_t *)c.d_wrows;
+#define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep)
+            if (ep.mode == OUT_NCDHW_F32) { if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD); else ANX_ROWS_LAUNCH(EPI_F32); }
+            else ANX_ROWS_LAUNCH(EPI_PADDED);
+#undef ANX_ROWS_LAUNCH
+            break;
+        }
         if (force_simt) {
             ActView src = view_of(e, p, c.src_buf, 0);
             const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
@@ -789,6 +812,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     e->num_sms = prop.multiProcessorCount;
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
     if (const char *xl = getenv("ANX_X_LEAD")) e->x_lead = atoi(xl);
+    if (const char *rw = getenv("ANX_ROWS")) e->use_rows = atoi(rw);
     build_program(e);
     build_taps(e);
     for (auto &c : e->convs) {
@@ -800,6 +824,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     ANX_SMEM(conv3_umma_kernel<EPI_PADDED>); ANX_SMEM(conv3_umma_kernel<EPI_POOL>); ANX_SMEM(conv3_umma_kernel<EPI_D2S>);
     ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
     ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>);
+    ANX_SMEM(conv3_rows_kernel<EPI_PADDED>); ANX_SMEM(conv3_rows_kernel<EPI_F32>); ANX_SMEM(conv3_rows_kernel<EPI_F32_HEAD>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
     ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
 #undef ANX_SMEM
@@ -827,6 +852,7 @@ void anx_engine_destroy(anx_engine *e) {
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
+        if (c.d_wrows) cudaFree(c.d_wrows);
         if (c.d_bias) cudaFree(c.d_bias);
     }
     delete e;
@@ -908,6 +934,28 @@ static anx_status upload_conv(anx_engine *e, ConvLayer &c, const std::vector<flo
         c.wpack_bytes = pk.size() * sizeof(uint16_t);
         ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
         ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
+        if (c.d_wrows) { cudaFree(c.d_wrows); c.d_wrows = nullptr; }
+        if (c.fold && c.cin == 16 && c.ncols == 16 && c.n_splits == 1) {
+            // conv3_rows_kernel: image r (= input plane mod 3), tap dx, K half, row (j*3 + s)*16 + co holds
+            // w[co][ci][kz][ky][dx] with ky = 2 - j (output row i - ky) and kz = (r - s) mod 3 (z slot s)
+            std::vector<uint16_t> img((size_t)3 * ROWS_B_IMAGE_BYTES / 2, 0);
+            for (int r = 0; r < 3; ++r)
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int j = 0; j < 3; ++j)
+                        for (int s = 0; s < 3; ++s) {
+                            const int ky = 2 - j, kz = (r - s + 3) % 3;
+                            for (int o = 0; o < c.cout; ++o)
+                                for (int i = 0; i < 16; ++i) {
+                                    const float v = w[((size_t)o * c.cin + i) * 27 + kz * 9 + ky * 3 + dx];
+                                    const size_t row = (size_t)(j * 3 + s) * 16 + o;
+                                    const size_t idx = (size_t)r * (ROWS_B_IMAGE_BYTES / 2) + (size_t)dx * (ROWS_B_TAP_BYTES / 2) +
+                                                       ((size_t)(i / 8) * ROWS_N + row) * 8 + i % 8;
+                                    img[idx] = e->dt == DT_BF16 ? f32_to_bf16_rne(v) : f32_to_f16_rne(v);
+                                }
+                        }
+            ANX_CUDA(e, cudaMalloc(&c.d_wrows, img.size() * 2));
+            ANX_CUDA(e, cudaMemcpy(c.d_wrows, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        }
     }
     ANX_CUDA(e, cudaMalloc(&c.d_bias, c.ncols * sizeof(float)));
     ANX_CUDA(e, cudaMemcpy(c.d_bias, shift.data(), c.ncols * sizeof(float), cudaMemcpyHostToDevice));

@@ -511,3 +511,28 @@ def test_native_blend_kernel_matches_torch_accumulate():
     got = sliding_window_features(x.cuda(), (16, 16, 24), 4, pred, overlap=0.6, mode="gaussian", sigma_scale=0.25)
     assert got.shape == want.shape == (2, 3, 40, 37, 52)
     assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256)])
+def test_row_kernel_matches_generic_kernel(shape, monkeypatch):
+    """conv3_rows_kernel (dy and dz folded into N, lanes = one 128-voxel row) against the generic tile kernel
+    on the same packed 16-bit operands: only the fp32 summation order differs."""
+    cfg = small_cfg()
+    state = O.random_state(cfg, seed=13)
+    x = rand_input(shape, 19)
+    monkeypatch.setenv("ANX_ROWS", "0")
+    ref = make_engine(cfg, state).forward(x.cuda())
+    monkeypatch.setenv("ANX_ROWS", "1")
+    eng = make_engine(cfg, state)
+    got = eng.forward(x.cuda())
+    torch.cuda.synchronize()
+    r = rel_l2(got.cpu(), ref.cpu())
+    assert r < 3e-3, f"row kernel vs generic kernel: rel-L2 {r:.3e}"
+    check_against_oracle(cfg, state, x, got)
+    # fused head on the row kernel's fp32 epilogue
+    torch.manual_seed(1)
+    hw, hb = torch.randn(5, 16), torch.randn(5)
+    eng.set_head(hw, hb)
+    got_h = eng.forward(x.cuda())
+    want_h = torch.einsum("kc,ncdhw->nkdhw", hw.double(), got.cpu().double()) + hb.double().view(1, -1, 1, 1, 1)
+    assert rel_l2(got_h.cpu(), want_h) < 1e-5
