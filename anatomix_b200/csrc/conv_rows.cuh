@@ -59,7 +59,7 @@ struct RowsShared {
 };
 static_assert(offsetof(RowsShared, shift) % 16 == 0, "shift must be 16-byte aligned");
 
-template <int MODE>   // EPI_PADDED, EPI_F32 or EPI_F32_HEAD
+template <int MODE>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 or EPI_F32_HEAD
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -170,6 +170,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue
+        constexpr bool SEEDED = MODE == EPI_SEEDED;
+        constexpr bool POOL = MODE == EPI_POOL;
+        constexpr bool PADDED = MODE == EPI_PADDED || SEEDED || POOL;
         const int q = warp & 3;                    // TMEM lane quadrant
         const int h = (warp - 2) >> 2;             // rows {2h, 2h + 1} of each strip
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -178,51 +181,130 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         const size_t vol = (size_t)Dd * Hh * Ww;
         float sd[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sd[i] = sh->shift[i];
-        // every accumulator column starts from the channel shift
-        for (int s = 0; s < 2; ++s) {
-            for (int r = 0; r < 2; ++r)
-                for (int slot = 0; slot < 3; ++slot)
-                    tmem_st16(lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + slot) * 16, sd);
+        for (int i = 0; i < 16; ++i) sd[i] = SEEDED ? 0.0f : sh->shift[i];
+        // SEEDED: the accumulators of output plane o start from stored partial sums (the low-resolution half of
+        // a decoder conv, see engine.cu "upconv") instead of the channel shift
+        const size_t sgstride = SEEDED ? (size_t)ep.seed_src.pitch * (Hh + 2) * (Dd + 2) : 0;
+        auto load_seed = [&](bool valid, int n_, int z_, int y_, int x_, uint4 &s0, uint4 &s1) {
+            s0 = s1 = make_uint4(0u, 0u, 0u, 0u);
+            if (SEEDED && valid) {
+                const uint4 *ps = ep.seed_src.at(n_, 0, z_ + 1, y_ + 1, x_ + 1);
+                s0 = __ldg(ps);
+                s1 = __ldg(ps + sgstride);
+            }
+        };
+        auto seed_store = [&](uint32_t col, const uint4 &s0, const uint4 &s1) {
+            if constexpr (SEEDED) {
+                float sv[16];
+                unpack_x8(s0, sv, ep.dt);
+                unpack_x8(s1, sv + 8, ep.dt);
+                tmem_st16(col, sv);
+            } else {
+                tmem_st16(col, sd);
+            }
+        };
+        // start: slot 0 holds the seeds of the first unit's plane 0 (slots 1 and 2 are re-seeded by the two
+        // phantom planes before a real plane touches them); without seeds every column starts from the shift
+        {
+            int n, x0, y0, z0;
+            decode(blockIdx.x < g.total_units ? blockIdx.x : 0, n, x0, y0, z0);
+            for (int s = 0; s < 2; ++s)
+                for (int r = 0; r < 2; ++r) {
+                    uint4 s0, s1;
+                    load_seed(blockIdx.x < g.total_units, n, z0, y0 + s * ROWS_BY + 2 * h + r, x0 + lx, s0, s1);
+                    for (int slot = 0; slot < 3; ++slot) {
+                        const uint32_t col = lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + slot) * 16;
+                        if (slot == 0) seed_store(col, s0, s1);
+                        else tmem_st16(col, sd);
+                    }
+                }
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive(&sh->drained[0]); mbar_arrive(&sh->drained[1]); }
 
+        uint32_t held[2][8];                        // POOL: row-pair maxima of the even plane of a z pair, per strip
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) held[s][i] = 0u;
+
+        // SEEDED: seeds the drain of (plane p, strip s) writes back -- those of the plane that uses the slot
+        // next: o + 3 of the same unit, or plane 0 of the next unit after the last plane.  They are loaded one
+        // drain ahead (`nsq`), so the L2 / HBM latency hides behind a drain's worth of work.
+        auto seeds_for = [&](int p_, int s_, int n_, int x0_, int y0_, int z0_, bool nvalid, int nn_, int nx0_, int ny0_,
+                             int nz0_, uint4 (&out)[2][2]) {
+            const int o_ = p_ - 2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int yo = s_ * ROWS_BY + 2 * h + r;
+                if (o_ + 3 < g.zs) load_seed(true, n_, z0_ + o_ + 3, y0_ + yo, x0_ + lx, out[r][0], out[r][1]);
+                else if (o_ == g.zs - 1) load_seed(nvalid, nn_, nz0_, ny0_ + yo, nx0_ + lx, out[r][0], out[r][1]);
+                else load_seed(false, 0, 0, 0, 0, out[r][0], out[r][1]);
+            }
+        };
+        uint4 nsq[2][2];
+        if constexpr (SEEDED) {
+            int n, x0, y0, z0;
+            decode(blockIdx.x < g.total_units ? blockIdx.x : 0, n, x0, y0, z0);
+            seeds_for(0, 0, n, x0, y0, z0, false, 0, 0, 0, 0, nsq);     // p = 0 never needs the next unit
+        }
+
         uint32_t ka = 0;
         for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
             int n, x0, y0, z0;
             decode(unit, n, x0, y0, z0);
             const int x = x0 + lx;
+            const int next_unit = unit + (int)gridDim.x;
+            const bool nvalid = next_unit < g.total_units;
+            int nn = 0, nx0 = 0, ny0 = 0, nz0 = 0;
+            if (SEEDED && nvalid) decode(next_unit, nn, nx0, ny0, nz0);
             for (int p = 0; p < planes; ++p, ++ka) {
                 const int o = p - 2;                               // output plane completed by input plane p
                 const int slot = (o + 3) % 3;
                 const int z = z0 + o;
+#pragma unroll
                 for (int s = 0; s < 2; ++s) {
+                    // seeds of the plane that uses this slot next: o + 3 of this unit, or plane 0 of the next unit
+                    uint4 sq[2][2];
+                    if constexpr (SEEDED) {
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) { sq[r][0] = nsq[r][0]; sq[r][1] = nsq[r][1]; }
+                        // the drain after this one: the other strip, the next plane, or the first drain of the next unit
+                        if (s == 0) seeds_for(p, 1, n, x0, y0, z0, nvalid, nn, nx0, ny0, nz0, nsq);
+                        else if (p + 1 < planes) seeds_for(p + 1, 0, n, x0, y0, z0, nvalid, nn, nx0, ny0, nz0, nsq);
+                        else if (nvalid) seeds_for(0, 0, nn, nx0, ny0, nz0, false, 0, 0, 0, 0, nsq);
+                    }
                     mbar_wait(&sh->acc_ready[s], ka & 1, 25);
                     tc_fence_after();
+                    uint32_t pm[8];                                // POOL: maximum over this warp's two rows
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const int yo = 2 * h + r;
                         const uint32_t col = lane_base + s * ROWS_STRIP_COLS + (yo * 3 + slot) * 16;
                         __syncwarp();
                         if (o < 0) {                               // phantom plane below the segment: discard
-                            tmem_st16(col, sd);
+                            seed_store(col, sq[r][0], sq[r][1]);
                             continue;
                         }
                         uint32_t rr[16];
                         tmem_ld16_nowait(col, rr);
                         tmem_wait_ld();
                         tmem_ld_ready16(rr);
-                        tmem_st16(col, sd);
-                        if (g.ablate & 2) continue;
+                        seed_store(col, sq[r][0], sq[r][1]);
                         const int y = y0 + s * ROWS_BY + yo;
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = activate(__uint_as_float(rr[i]), ep.act, ep.slope);
-                        if constexpr (MODE == EPI_PADDED) {
+                        if constexpr (PADDED) {
                             const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
+                            if constexpr (POOL) {
+                                const uint32_t pk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) pm[i] = r == 0 ? pk[i] : max16x2(pm[i], pk[i], ep.dt);
+                            }
+                            if (g.ablate & 2) continue;
                             const size_t rowp = (size_t)ep.dst.pitch, plane = rowp * (Hh + 2), gstride = plane * (Dd + 2);
                             uint4 *pd = ep.dst.at(n, 0, z + 1, y + 1, x + 1);
                             *pd = q0;
@@ -235,11 +317,13 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                                 store_mirrors(pd + gstride, q1, mdz, mdy, mdx, rowp, plane);
                             }
                         } else if constexpr (MODE == EPI_F32) {
+                            if (g.ablate & 2) continue;
                             float *po = ep.out_f32 + (size_t)n * ep.cout * vol + ((size_t)z * Hh + y) * Ww + x;
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
                                 if (i < ep.cout) po[(size_t)i * vol] = v[i];
                         } else {
+                            if (g.ablate & 2) continue;
                             const float *hb = sh->shift + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
                             float *po = ep.out_f32 + (size_t)n * ep.head_nc * vol + ((size_t)z * Hh + y) * Ww + x;
 #pragma unroll 2
@@ -257,7 +341,27 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                             }
                         }
                     }
-                    if (p == planes - 1) {          // phantom planes above the segment: back to the shift
+                    if constexpr (POOL) {
+                        // 2x2x2 max pooling (reference network.py:297,368) of the values just stored: y pair = this
+                        // warp's two rows, z pair = planes (o, o + 1) via `held`, x pair = neighbouring lanes
+                        if (o >= 0) {
+                            if (!(o & 1)) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) held[s][i] = pm[i];
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    pm[i] = max16x2(pm[i], held[s][i], ep.dt);
+                                    pm[i] = max16x2(pm[i], __shfl_xor_sync(0xffffffffu, pm[i], 1), ep.dt);
+                                }
+                                if (!(lane & 1) && !(g.ablate & 2))
+                                    store_padded_groups(ep.pool_dst, n, 0, 2, z >> 1, (y0 + s * ROWS_BY + 2 * h) >> 1, x >> 1,
+                                                        make_uint4(pm[0], pm[1], pm[2], pm[3]),
+                                                        make_uint4(pm[4], pm[5], pm[6], pm[7]));
+                            }
+                        }
+                    }
+                    if (p == planes - 1) {          // phantom planes above the segment: neutral again
 #pragma unroll
                         for (int r = 0; r < 2; ++r)
 #pragma unroll

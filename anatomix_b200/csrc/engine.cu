@@ -658,7 +658,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
         if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0))
             return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path without a fused gather");
-        if (!force_simt && e->use_rows && c.d_wrows && !g.fuse_pool && !ep.seed_on && !ep.stats && !ep.d2s_cout &&
+        if (!force_simt && e->use_rows && c.d_wrows && !(g.fuse_pool && ep.pool_kind != 0) && !ep.stats && !ep.d2s_cout &&
+            !((e->use_rows & 2) && (g.fuse_pool || ep.seed_on)) &&      // ANX_ROWS=3: plain / fp32 variants only
             ep.n_peers == 0 && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
             RowsGeom rg{};
             rg.N = g.N; rg.D = g.D; rg.H = g.H; rg.W = g.W;
@@ -674,6 +675,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const uint8_t *wr = (const uint8_t *)c.d_wrows;
 #define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep)
             if (ep.mode == OUT_NCDHW_F32) { if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD); else ANX_ROWS_LAUNCH(EPI_F32); }
+            else if (ep.seed_on) ANX_ROWS_LAUNCH(EPI_SEEDED);
+            else if (g.fuse_pool) ANX_ROWS_LAUNCH(EPI_POOL);
             else ANX_ROWS_LAUNCH(EPI_PADDED);
 #undef ANX_ROWS_LAUNCH
             break;
@@ -825,6 +828,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
     ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>);
     ANX_SMEM(conv3_rows_kernel<EPI_PADDED>); ANX_SMEM(conv3_rows_kernel<EPI_F32>); ANX_SMEM(conv3_rows_kernel<EPI_F32_HEAD>);
+    ANX_SMEM(conv3_rows_kernel<EPI_SEEDED>); ANX_SMEM(conv3_rows_kernel<EPI_POOL>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
     ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
 #undef ANX_SMEM
