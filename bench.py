@@ -59,7 +59,7 @@ def weights():
 
 
 def ncu_traffic_bytes():
-    """DRAM bytes (read + write) of the conv kernel's launches in one 8x128^3 forward, from the committed
+    """DRAM bytes (read + write) of the conv kernels' launches in one 8x128^3 forward, from the committed
     ncu --set full capture (profiles/r1_traffic.json); None when that file is missing."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(path):
@@ -333,7 +333,8 @@ def main():
                     "h2d_bytes_per_step": B * VOL ** 3 * 4, "d2h_bytes_per_step": B * 16 * VOL ** 3 * 4},
             "gpu_launches": eng.launches_per_forward(B, VOL, VOL, VOL) * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv3_umma_kernel (%d launches per forward)" % sum(
+            "roofline": {"bound": "tensor", "kernel": "conv3_umma_kernel + conv3_rows_kernel, the two tcgen05 conv kernels "
+                                                      "(%d launches per forward)" % sum(
                              1 for n in order if "conv" in n and not n.startswith("conv0_")),
                          "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained)",

@@ -1,5 +1,5 @@
 """Two 8x128^3 forwards of the 6M network (the second one is the one to capture under ncu):
-    ncu --set full --clock-control none --import-source on -k regex:conv3_umma --launch-skip 20 --launch-count 20 \
+    ncu --set full --clock-control none --import-source on -k regex:'conv3_umma|conv3_rows|stem_umma' --launch-skip 21 --launch-count 21 \
         -o gpurun_out/fwd python tools/ncu_forward.py
 """
 import os, sys
