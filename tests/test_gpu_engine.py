@@ -536,3 +536,20 @@ def test_row_kernel_matches_generic_kernel(shape, monkeypatch):
     got_h = eng.forward(x.cuda())
     want_h = torch.einsum("kc,ncdhw->nkdhw", hw.double(), got.cpu().double()) + hb.double().view(1, -1, 1, 1, 1)
     assert rel_l2(got_h.cpu(), want_h) < 1e-5
+
+
+@pytest.mark.parametrize("cfgkw,flags", [
+    (dict(norm="none", activation="lrelu"), 0),            # no norm (zero shift), leaky ReLU in the row epilogue
+    (dict(), 2),                                           # ANX_FLAG_STORE_FP16: fp16 operands through the row kernel
+    (dict(num_downs=1, output_nc=5), 0),                   # 5 output channels: masked fp32 stores of the last conv
+])
+def test_row_kernel_variants(cfgkw, flags):
+    cfg = small_cfg(**cfgkw)
+    state = O.random_state(cfg, seed=21)
+    x = rand_input((1, 1, 16, 24, 128), 23)
+    got = make_engine(cfg, state, flags=flags).forward(x.cuda())
+    torch.cuda.synchronize()
+    want = O.unet_forward(cfg, state, x)
+    assert torch.isfinite(got).all()
+    r, c = rel_l2(got.cpu(), want), min_cosine(got.cpu(), want)
+    assert r <= LOOSE_REL and c >= LOOSE_COS, f"rel-L2 {r:.3e}, min cosine {c:.5f}"
