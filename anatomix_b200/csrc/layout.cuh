@@ -132,7 +132,8 @@ struct ConvGeom {
     uint32_t smem_bytes;
     int fuse_pool;          // this launch also writes the pooled tensor (needs bz % 4 == 0)
     int b_static;           // 1: one B slab serves every tile; loaded once per CTA, never recycled
-    uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load
+    uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load,
+                            // 16 every tap reads the brick origin, 32 128-byte aligned core matrices (results are wrong)
 };
 
 }   // namespace anx
