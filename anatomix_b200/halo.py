@@ -33,6 +33,25 @@ from .dist import exchange_halo_planes, slab_bounds
 from .engine import Engine
 
 
+def run_slab_program(steps, run_step, step_stats, all_reduce_stats, exchange, world: int) -> None:
+    """The per-launch protocol of a depth slab, independent of what executes the launches.
+
+    ``steps``: ``[(kind, out_buffer, out_group_offset, out_groups, name)]`` as from `Engine.step_table`.
+    After launch i: if it accumulated InstanceNorm sums (``step_stats(i)`` is not None) those are summed over
+    the slabs -- the normalisation launch that follows needs whole-volume statistics, and the raw planes need no
+    exchange because the normalised ones are swapped after that launch; otherwise, if the launch produced an
+    activation tensor, neighbours swap its boundary planes."""
+    for i, (kind, buf, goff, groups, name) in enumerate(steps):
+        run_step(i)
+        if world == 1:
+            continue
+        stats = step_stats(i)
+        if stats is not None:
+            all_reduce_stats(stats)
+        elif buf >= 0:
+            exchange(buf, goff, groups)
+
+
 def slab_input_with_halo(volume: torch.Tensor, z_lo: int, z_hi: int) -> torch.Tensor:
     """``volume[:, :, z_lo-1 : z_hi+1]`` with reflect copies where the slab touches a
     global face (plane -1 -> plane 1, plane D -> plane D-2)."""
@@ -82,18 +101,17 @@ class DepthSlabExtractor:
         out = torch.empty((n, self.cfg["output_nc"], d, h, w), dtype=torch.float32, device=self.engine.device)
         ws = self.engine.workspace(n, d, h, w)
         table = self.engine.buffer_table(n, d, h, w)
-        for i, (kind, buf, goff, groups, name) in enumerate(self.steps):
-            self.engine.run_steps(x, out, i, i + 1)
-            if self.world == 1:
-                continue
+        def stats_view(i):
             off, nbytes = self.engine.step_stats(i, n, d, h, w)
-            if nbytes:
-                # InstanceNorm: whole-volume statistics before the normalisation step that follows; the raw
-                # planes need no exchange, the normalised ones are swapped after that step
-                dist.all_reduce(ws[off:off + nbytes].view(torch.float64), group=self.group)
-                continue
-            if buf >= 0:
-                self._exchange(ws, table, buf, goff, groups, n, d, h, w)
+            return ws[off:off + nbytes].view(torch.float64) if nbytes else None
+
+        run_slab_program(
+            self.steps,
+            run_step=lambda i: self.engine.run_steps(x, out, i, i + 1),
+            step_stats=stats_view,
+            all_reduce_stats=lambda t: dist.all_reduce(t, group=self.group),
+            exchange=lambda buf, goff, groups: self._exchange(ws, table, buf, goff, groups, n, d, h, w),
+            world=self.world)
         if not gather or self.world == 1:
             return out
         # slabs have equal depth unless depth/unit is not a multiple of world: gather plane-major, then permute back

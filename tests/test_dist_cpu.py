@@ -76,6 +76,71 @@ def _worker(rank, world, port, ragged):
         dist.destroy_process_group()
 
 
+def _slab_worker(rank, world, port):
+    """The slab protocol (anatomix_b200.halo.run_slab_program) on a toy two-layer network executed with torch
+    ops: z-conv -> whole-volume normalisation -> z-conv -> normalisation, depth split over two ranks with a
+    one-plane shell, against the unsplit computation."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from anatomix_b200.halo import run_slab_program
+        D, P = 8, 6                                            # depth, voxels per plane
+        vol = torch.rand(D, P, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+        taps = torch.tensor([0.25, 0.5, -0.75], dtype=torch.float64)
+
+        def zconv(padded):                                     # valid 3-tap correlation along z of a shelled tensor
+            return taps[0] * padded[:-2] + taps[1] * padded[1:-1] + taps[2] * padded[2:]
+
+        def reflect_shell(t):                                  # [d, P] -> [d + 2, P] with reflect copies
+            return torch.cat([t[1:2], t, t[-2:-1]])
+
+        # unsplit reference
+        a = zconv(reflect_shell(vol)); a = (a - a.mean()) / a.std(unbiased=False)
+        b = zconv(reflect_shell(a)); want = (b - b.mean()) / b.std(unbiased=False)
+
+        lo, hi = (0, D // 2) if rank == 0 else (D // 2, D)
+        d = hi - lo
+        idx = [lo - 1 if lo > 0 else 1] + list(range(lo, hi)) + [hi if hi < D else D - 2]
+        bufs = {0: vol[idx].clone(), 1: torch.zeros(d + 2, P, dtype=torch.float64), 2: torch.zeros(d + 2, P, dtype=torch.float64)}
+        sums = {1: torch.zeros(2, dtype=torch.float64), 3: torch.zeros(2, dtype=torch.float64)}
+        steps = [(1, 1, 0, 1, "conv"), (4, 1, 0, 1, "norm"), (1, 2, 0, 1, "conv"), (4, 2, 0, 1, "norm")]
+        src_of = {0: 0, 2: 1}
+
+        def run_step(i):
+            kind, buf = steps[i][0], steps[i][1]
+            if kind == 1:                                      # conv: raw output + reflect shell + local sums
+                y = zconv(bufs[src_of[i]])
+                bufs[buf] = reflect_shell(y)
+                sums[i + 1][0], sums[i + 1][1] = y.sum(), (y * y).sum()
+            else:                                              # normalise in place, shell included
+                s, q = sums[i]
+                mean = s / (D * P)
+                var = q / (D * P) - mean * mean
+                bufs[buf] = (bufs[buf] - mean) / var.sqrt()
+
+        def exchange(buf, goff, groups):
+            t = bufs[buf]
+            lo_in, hi_in = torch.empty(P, dtype=torch.float64), torch.empty(P, dtype=torch.float64)
+            exchange_halo_planes(t[1].contiguous(), t[d].contiguous(), lo_in, hi_in, rank, world)
+            if rank > 0:
+                t[0] = lo_in
+            if rank < world - 1:
+                t[d + 1] = hi_in
+
+        run_slab_program(steps, run_step, lambda i: sums[i + 1] if steps[i][0] == 1 else None,
+                         lambda t: dist.all_reduce(t), exchange, world)
+        assert torch.allclose(bufs[2][1:-1], want[lo:hi], atol=1e-12), (bufs[2][1:-1] - want[lo:hi]).abs().max()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_slab_protocol_with_whole_volume_statistics():
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_slab_worker, args=(2, port), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("ragged", [False, True])
 def test_two_rank_gloo_sharding_and_halo(ragged):
     port = 29500 + (os.getpid() % 2000) + (1 if ragged else 0)
