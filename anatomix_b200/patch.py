@@ -64,10 +64,16 @@ def patch_reference(unet_cls=None):
             cfg = self.__dict__.get("_anx_cfg")
             if cfg is None:
                 cfg = _cfg_from_reference_module(self)
+                binding = ModuleBinding(self, cfg)
                 self.__dict__["_anx_cfg"] = cfg
-                self.__dict__["_anx_binding"] = ModuleBinding(self, cfg)
-            if ineligible_reason(self, cfg, input, layers) is None:
-                return self.__dict__["_anx_binding"].forward(input)
+                self.__dict__["_anx_binding"] = binding
+                self.__dict__["_engine_binding"] = lambda: binding     # what ineligible_reason asks tapped calls for
+            tapping = len(layers) > 0
+            if not (tapping and verbose) and ineligible_reason(self, cfg, input, layers) is None:
+                binding = self.__dict__["_anx_binding"]
+                if tapping:       # feature taps the engine stores (network.py:475-529)
+                    return binding.forward_taps(input, layers, encode_only)
+                return binding.forward(input)
         return stock_forward(self, input, layers, encode_only, verbose)
 
     unet_cls.forward = forward
