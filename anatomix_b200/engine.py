@@ -10,6 +10,7 @@ module's parameters.  All arithmetic of an eligible forward happens inside
 from __future__ import annotations
 
 import ctypes as C
+import operator
 from typing import Dict, Optional
 
 import torch
@@ -379,7 +380,14 @@ class ModuleBinding:
         """(engine, missing): the engine variant that stores every tapped slot.  The default program
         evaluates the upsampled half of the last decoder conv at low resolution and never builds that
         concat tensor; a tap there uses the single-launch variant (ANX_FLAG_NO_UPCONV)."""
-        valid = [i for i in layers if isinstance(i, int) and 0 <= i < len(self.module.model)]
+        valid = []
+        for i in layers:            # the reference matches slots with `layer_id in layers`: any integer-like entry counts
+            try:
+                k = operator.index(i)
+            except TypeError:
+                continue
+            if 0 <= k < len(self.module.model):
+                valid.append(k)
         eng, missing = None, valid
         for flags in (0, _lib.FLAG_NO_UPCONV):
             eng = self.engine_for(device, flags)
