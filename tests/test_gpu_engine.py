@@ -513,7 +513,7 @@ def test_native_blend_kernel_matches_torch_accumulate():
     assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256)])
+@pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256), (3, 1, 16, 8, 128), (1, 1, 48, 40, 128)])
 def test_row_kernel_matches_generic_kernel(shape, monkeypatch):
     """conv3_rows_kernel (dy and dz folded into N, lanes = one 128-voxel row) against the generic tile kernel
     on the same packed 16-bit operands: only the fp32 summation order differs."""
