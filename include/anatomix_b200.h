@@ -143,7 +143,8 @@ anx_status anx_engine_run_steps(anx_engine *engine, const float *in_ncdhw, float
  * over depth_total x H x W).  Every conv that feeds an InstanceNorm accumulates its sums into a block of
  * doubles [n][cout rounded up to 16][sum, sum of squares] inside the workspace; `anx_engine_step_stats`
  * gives that block for a step (bytes = 0 for any other step), and the caller all-reduces it over the
- * slabs between that step and the normalisation step that follows.  depth_total = 0 switches the mode off. */
+ * slabs between that step and the normalisation step that follows.  depth_total = 0 switches the mode off.
+ * anx_engine_set_slab changes engine state: call it between forwards, not during one. */
 anx_status anx_engine_set_slab(anx_engine *engine, int32_t has_lower_neighbour,
                                int32_t has_upper_neighbour, int32_t depth_total);
 anx_status anx_engine_step_stats(const anx_engine *engine, int32_t step, int32_t n, int32_t d,
@@ -179,7 +180,8 @@ anx_status anx_engine_forward_host(anx_engine *engine, const float *in_host, flo
  * `pred * downscale_feat_scalar` (anatomix/registration/run_convex_adam_with_network_feats.py:166-167).
  * `weight` is fp32 [head_nc][output_nc] (the Conv3d weight with its 1x1x1 tail dropped), `bias`
  * fp32 [head_nc] or NULL.  Afterwards every forward writes fp32 [N, head_nc, D, H, W]
- * (anx_engine_out_channels).  head_nc = 0 removes the head.  Needs output_nc <= 16, head_nc <= 32. */
+ * (anx_engine_out_channels).  head_nc = 0 removes the head.  Needs output_nc <= 16, head_nc <= 32.
+ * Like anx_engine_set_conv it changes engine state: not thread-safe against concurrent forwards. */
 anx_status anx_engine_set_head(anx_engine *engine, int32_t head_nc, const float *weight,
                                const float *bias, int32_t location);
 int32_t anx_engine_out_channels(const anx_engine *engine);
