@@ -150,13 +150,15 @@ def exchange_halo_planes(lo_plane_out: torch.Tensor, hi_plane_out: torch.Tensor,
     rank-1 and my last interior plane to rank+1; receive their boundary planes into
     ``lo_plane_in`` (from rank-1) and ``hi_plane_in`` (from rank+1).  Ranks at the
     global faces skip the missing neighbour (their shell keeps the reflect copy)."""
+    # `rank` / `world` are GROUP-local; P2POp addresses peers by GLOBAL rank
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     ops = []
     if rank > 0:
-        ops.append(dist.P2POp(dist.isend, lo_plane_out, rank - 1, group))
-        ops.append(dist.P2POp(dist.irecv, lo_plane_in, rank - 1, group))
+        ops.append(dist.P2POp(dist.isend, lo_plane_out, peer(rank - 1), group))
+        ops.append(dist.P2POp(dist.irecv, lo_plane_in, peer(rank - 1), group))
     if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, hi_plane_out, rank + 1, group))
-        ops.append(dist.P2POp(dist.irecv, hi_plane_in, rank + 1, group))
+        ops.append(dist.P2POp(dist.isend, hi_plane_out, peer(rank + 1), group))
+        ops.append(dist.P2POp(dist.irecv, hi_plane_in, peer(rank + 1), group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 import operator
+import os
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -175,19 +177,37 @@ class Engine:
             f"multiple of {unit} and at least {2 * unit} (the reference fails on such shapes too)")
 
     def workspace(self, n, d, h, w) -> torch.Tensor:
-        key = (n, d, h, w)
+        """Activation workspace for one shape ON THE CURRENT STREAM: forwards of the same shape queued on
+        different streams (DataParallel threads, user side streams) get distinct buffers, so they never race
+        on the activations (include/anatomix_b200.h: concurrent forwards need distinct workspaces)."""
+        stream = torch.cuda.current_stream(self.device)
+        key = (stream.cuda_stream, n, d, h, w)
         ws = self._workspaces.get(key)
         if ws is None:
             need = self.workspace_bytes(n, d, h, w)
             if need == 0:
                 raise self._shape_error((n, self.input_nc, d, h, w))
             if len(self._workspaces) >= 4:
-                self._workspaces.pop(next(iter(self._workspaces)))
+                old_key = next(iter(self._workspaces))
+                old = self._workspaces.pop(old_key)
+                # work queued on the evicted workspace's stream may still read it: tell the caching
+                # allocator not to hand the block out before that stream has passed this point
+                old.record_stream(torch.cuda.ExternalStream(old_key[0], device=self.device)
+                                  if old_key[0] else torch.cuda.default_stream(self.device))
+                del old
             # zeroed once: the unused lead / tail voxels of every padded row then stay finite and equal
             # between runs (halo plane exchanges and buffer dumps copy them along)
-            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
             self._workspaces[key] = ws
         return ws
+
+    def _check_out(self, out: torch.Tensor, shape, what="out"):
+        if not isinstance(out, torch.Tensor) or tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 \
+                or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"`{what}` must be a contiguous fp32 tensor of shape {tuple(shape)} on {self.device}; "
+                             f"got {tuple(out.shape)} {out.dtype} on {out.device}"
+                             f"{'' if out.is_contiguous() else ' (non-contiguous)'}")
 
     def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 NCDHW CUDA tensor in, fp32 NCDHW CUDA tensor out, queued on the
@@ -203,6 +223,8 @@ class Engine:
         ws = self.workspace(n, d, h, w)
         if out is None:
             out = torch.empty((n, self.output_nc, d, h, w), dtype=torch.float32, device=self.device)
+        else:
+            self._check_out(out, (n, self.output_nc, d, h, w))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self._check(self.lib.anx_engine_forward(
@@ -226,7 +248,15 @@ class Engine:
     def forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
                      dev_out: torch.Tensor):
         """End-to-end call on (pinned) host buffers; see anx_engine_forward_host."""
+        if x_host.dim() != 5 or x_host.shape[1] != self.input_nc:
+            raise ValueError(f"expected host input [N, {self.input_nc}, D, H, W], got {tuple(x_host.shape)}")
         n, _, d, h, w = x_host.shape
+        for t, shape, what in ((x_host, (n, self.input_nc, d, h, w), "x_host"),
+                               (out_host, (n, self.output_nc, d, h, w), "out_host")):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"`{what}` must be a contiguous fp32 CPU tensor of shape {shape}")
+        self._check_out(dev_in, (n, self.input_nc, d, h, w), "dev_in")
+        self._check_out(dev_out, (n, self.output_nc, d, h, w), "dev_out")
         ws = self.workspace(n, d, h, w)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -300,6 +330,44 @@ class Engine:
 
 
 # --------------------------------------------------------------------- eligibility
+def _has_hooks(module: nn.Module) -> bool:
+    """True when any submodule carries forward hooks / pre-hooks: the engine never calls the submodules,
+    so such a model must run the stock loop for the hooks to fire."""
+    for m in module.modules():
+        if m._forward_hooks or m._forward_pre_hooks:
+            return True
+    return False
+
+
+def module_ineligible_reason(module: nn.Module, cfg: dict, device: torch.device) -> Optional[str]:
+    """The module-side half of the eligibility test (configuration, modes, parameters, hooks)."""
+    if cfg["pad_type"] != "reflect" or not cfg["doubleconv"] or not cfg["use_skip_connection"] \
+            or cfg["residual_connection"] or cfg["final_act"] != "none":
+        return "non-released topology flags"
+    if cfg["norm"] == "batch":
+        # the mode of every BatchNorm submodule counts, not only the top-level flag: `model.model[1].train()`
+        # on an eval model makes that layer use batch statistics in the reference
+        if module.training or any(m.training for m in module.modules()
+                                  if isinstance(m, nn.modules.batchnorm._BatchNorm)):
+            return "BatchNorm in train mode uses batch statistics"
+    elif cfg["norm"] not in ("none", "instance"):
+        return f"norm {cfg['norm']!r} is not handled by the engine"
+    if cfg["activation"] not in ("relu", "lrelu", "none"):
+        return "activation not supported"
+    if cfg["pooling"] not in ("Max", "Avg") or cfg["interp"] not in ("nearest", "trilinear"):
+        return "pooling / interpolation not supported"
+    widths = [cfg["ngf"] << i for i in range(cfg["num_downs"] + 1)]
+    if cfg["ngf"] % 16 != 0 or cfg["ngf"] > 64 or widths[-1] > 1024 or any(w > 256 and w % 256 for w in widths) \
+            or cfg["input_nc"] > 4 or cfg["output_nc"] > 256:
+        return "channel widths outside the tensor-core kernel's range"
+    for t in list(module.parameters()) + list(module.buffers()):
+        if t.is_floating_point() and (t.dtype != torch.float32 or t.device != device):
+            return "parameters are not fp32 on the input's device (the reference raises here)"
+    if _has_hooks(module):
+        return "forward hooks are registered on the module or a submodule"
+    return None
+
+
 def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[str]:
     """Why a call must stay on the stock torch path, or None if the engine takes
     it."""
@@ -313,22 +381,9 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
         return "autograd is recording"
     if torch.is_autocast_enabled():
         return "autocast region"
-    if cfg["pad_type"] != "reflect" or not cfg["doubleconv"] or not cfg["use_skip_connection"] \
-            or cfg["residual_connection"] or cfg["final_act"] != "none":
-        return "non-released topology flags"
-    if cfg["norm"] == "batch":
-        if module.training:
-            return "BatchNorm in train mode uses batch statistics"
-    elif cfg["norm"] not in ("none", "instance"):
-        return f"norm {cfg['norm']!r} is not handled by the engine"
-    if cfg["activation"] not in ("relu", "lrelu", "none"):
-        return "activation not supported"
-    if cfg["pooling"] not in ("Max", "Avg") or cfg["interp"] not in ("nearest", "trilinear"):
-        return "pooling / interpolation not supported"
-    widths = [cfg["ngf"] << i for i in range(cfg["num_downs"] + 1)]
-    if cfg["ngf"] % 16 != 0 or cfg["ngf"] > 64 or widths[-1] > 1024 or any(w > 256 and w % 256 for w in widths) \
-            or cfg["input_nc"] > 4 or cfg["output_nc"] > 256:
-        return "channel widths outside the tensor-core kernel's range"
+    why = module_ineligible_reason(module, cfg, x.device)
+    if why is not None:
+        return why
     if x.shape[1] != cfg["input_nc"]:
         return "channel mismatch"
     unit = 1 << cfg["num_downs"]
@@ -338,27 +393,90 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
         return "input is not fp32"
     if len(layers) > 0:
         # feature taps (network.py:475-529): served when every tapped slot is a tensor the engine stores
-        missing = module._engine_binding().untappable(x.device, layers)
+        missing = binding_for(module, cfg).untappable(x.device, layers)
         if missing:
             return (f"feature tap at slot {missing[0]} is not materialised by the engine "
                     "(pre-norm conv outputs are folded into the weights)")
     return None
 
 
+# ------------------------------------------------------------------------ bindings
+# Engine bindings live OUTSIDE the modules they serve (weakly keyed by the module), so a model that has run on
+# the engine still deep-copies, pickles and `torch.save`s like the reference's: ctypes handles never enter a
+# module's `__dict__`.  A copy / unpickled module simply gets its own binding on its first eligible forward.
+_BINDINGS: "weakref.WeakKeyDictionary[nn.Module, ModuleBinding]" = weakref.WeakKeyDictionary()
+
+# In-place updates through `.data` (``p.data.copy_()``, ``init.normal_(m.weight.data)``: reference
+# pretraining_networks.py:695-713) bump neither `_version` nor the storage pointer, so the cheap stamp cannot see
+# them.  Every VERIFY_EVERY-th forward therefore also compares a device-side checksum of all parameters and
+# buffers (one fused reduction + one 8-byte readback); 1 = every forward.  `invalidate()` forces a re-pack.
+VERIFY_EVERY = max(1, int(os.environ.get("ANATOMIX_B200_VERIFY_EVERY", "32")))
+
+
+def tensors_stamp(tensors) -> tuple:
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+def tensors_checksum(tensors) -> tuple:
+    """Content fingerprint of a list of tensors: (sum, sum of squares weighted by position) as python floats;
+    one sync.  Catches `.data` edits the version counters miss."""
+    fl = [t.detach().reshape(-1).double() for t in tensors if t.is_floating_point() and t.numel()]
+    if not fl:
+        return (0.0, 0.0)
+    sums = torch.stack([f.sum() for f in fl])
+    sq = torch.stack([(f * f).sum() for f in fl])
+    k = torch.arange(1, len(fl) + 1, dtype=torch.float64, device=sums.device)
+    both = torch.stack([(sums * k).sum(), (sq * k).sum()]).cpu()
+    return (both[0].item(), both[1].item())
+
+
+class PackStamp:
+    """When do packed weights need a refresh?  Cheap test every call (storage pointers + version counters),
+    content checksum every `VERIFY_EVERY` calls and whenever `invalidate()` was called."""
+
+    def __init__(self):
+        self.stamp, self.checksum, self.calls, self.dirty = None, None, 0, True
+
+    def invalidate(self):
+        self.dirty = True
+
+    def needs_repack(self, tensors) -> bool:
+        st = tensors_stamp(tensors)
+        self.calls += 1
+        if self.dirty or st != self.stamp:
+            self.stamp, self.checksum, self.dirty = st, tensors_checksum(tensors), False
+            return True
+        if self.calls % VERIFY_EVERY == 0:
+            cs = tensors_checksum(tensors)
+            if cs != self.checksum:
+                self.checksum = cs
+                return True
+        return False
+
+
 class ModuleBinding:
     """Keeps one `Engine` per device in sync with a live ``nn.Module``: packed
     weights are rebuilt whenever a parameter or buffer changed (``_version`` bump
-    from ``load_state_dict`` / an optimizer step, or new storage from ``.to()``)."""
+    from ``load_state_dict`` / an optimizer step, new storage from ``.to()``, or -- checked every
+    `VERIFY_EVERY` forwards -- a content change made through ``.data``)."""
 
     def __init__(self, module: nn.Module, cfg: dict):
-        self.module = module
+        self._module = weakref.ref(module)
         self.cfg = cfg
         self.engines: Dict[tuple, Engine] = {}
-        self.stamps: Dict[tuple, tuple] = {}
+        self.stamps: Dict[tuple, PackStamp] = {}
 
-    def _stamp(self):
-        return tuple((t.data_ptr(), t._version) for t in
-                     list(self.module.parameters()) + list(self.module.buffers()))
+    @property
+    def module(self) -> nn.Module:
+        m = self._module()
+        if m is None:
+            raise RuntimeError("the module of this binding has been collected")
+        return m
+
+    def invalidate(self):
+        """Forces the next forward to re-pack the weights (after edits the stamp cannot see)."""
+        for s in self.stamps.values():
+            s.invalidate()
 
     def engine_for(self, device: torch.device, flags: int = 0) -> Engine:
         key = (device, flags)
@@ -366,10 +484,10 @@ class ModuleBinding:
         if eng is None:
             eng = Engine(self.cfg, device, flags)
             self.engines[key] = eng
-        stamp = self._stamp()
-        if self.stamps.get(key) != stamp:
-            eng.load_state(self.module.state_dict())
-            self.stamps[key] = stamp
+            self.stamps[key] = PackStamp()
+        m = self.module
+        if self.stamps[key].needs_repack(list(m.parameters()) + list(m.buffers())):
+            eng.load_state(m.state_dict())
         return eng
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -381,12 +499,13 @@ class ModuleBinding:
         evaluates the upsampled half of the last decoder conv at low resolution and never builds that
         concat tensor; a tap there uses the single-launch variant (ANX_FLAG_NO_UPCONV)."""
         valid = []
+        n_slots = len(self.module.model)
         for i in layers:            # the reference matches slots with `layer_id in layers`: any integer-like entry counts
             try:
                 k = operator.index(i)
             except TypeError:
                 continue
-            if 0 <= k < len(self.module.model):
+            if 0 <= k < n_slots:
                 valid.append(k)
         eng, missing = None, valid
         for flags in (0, _lib.FLAG_NO_UPCONV):
@@ -404,3 +523,21 @@ class ModuleBinding:
         eng, missing = self._tap_engine(x.device, layers)
         assert not missing, missing
         return eng.forward_taps(x, list(layers), encode_only)
+
+
+def binding_for(module: nn.Module, cfg: dict) -> ModuleBinding:
+    """The (lazily created) engine binding of a module; never stored on the module itself."""
+    b = _BINDINGS.get(module)
+    if b is None:
+        b = ModuleBinding(module, cfg)
+        _BINDINGS[module] = b
+    return b
+
+
+def invalidate(module: nn.Module) -> None:
+    """Call after editing parameters through ``.data`` (or any other way that bypasses autograd's version
+    counters) to make the next engine forward re-pack the weights immediately instead of at the next
+    periodic content check."""
+    b = _BINDINGS.get(module)
+    if b is not None:
+        b.invalidate()

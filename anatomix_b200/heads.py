@@ -17,6 +17,7 @@ modules, exactly like the reference.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections import OrderedDict
 from typing import Dict, Optional
 
@@ -27,6 +28,26 @@ import torch.nn.functional as F
 from . import _lib
 
 HEAD_MAX = 32          # csrc/layout.cuh
+
+# engines with a fused head, weakly keyed by the wrapper module (never stored on it: deepcopy / pickle /
+# torch.save of the wrapper keep working after the engine has run): {module: {device: (Engine, PackStamp)}}
+_HEAD_ENGINES: "weakref.WeakKeyDictionary[nn.Module, Dict[torch.device, tuple]]" = weakref.WeakKeyDictionary()
+
+
+def _head_engine(owner: nn.Module, unet: nn.Module, device, tensors, head_weight_fn):
+    """Engine of `unet` with the head returned by ``head_weight_fn() -> (weight, bias)`` fused in; re-packed
+    when any of `tensors` changed (same staleness rules as `anatomix_b200.engine.ModuleBinding`)."""
+    from .engine import Engine, PackStamp
+    per_dev = _HEAD_ENGINES.setdefault(owner, {})
+    eng, stamp = per_dev.get(device, (None, None))
+    if eng is None:
+        eng, stamp = Engine(unet._anx_cfg, device), PackStamp()
+        per_dev[device] = (eng, stamp)
+    if stamp.needs_repack(tensors):
+        eng.load_state(unet.state_dict())
+        w, b = head_weight_fn()
+        eng.set_head(w, b)
+    return eng
 
 
 class UnetOutBlock(nn.Module):
@@ -62,7 +83,6 @@ class FusedHeadSequential(nn.Sequential):
 
     def __init__(self, unet: nn.Module, head: nn.Module):
         super().__init__(unet, head)
-        self._engines: Dict[torch.device, tuple] = {}
 
     def fused_ineligible_reason(self, x) -> Optional[str]:
         unet, head = self[0], self[1]
@@ -81,17 +101,9 @@ class FusedHeadSequential(nn.Sequential):
         return None
 
     def _engine(self, device):
-        from .engine import Engine
         unet, conv = self[0], pointwise_conv_of(self[1])
-        stamp = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
-        eng, old = self._engines.get(device, (None, None))
-        if eng is None:
-            eng = Engine(unet._anx_cfg, device)
-        if old != stamp:
-            eng.load_state(unet.state_dict())
-            eng.set_head(conv.weight, conv.bias)
-            self._engines[device] = (eng, stamp)
-        return eng
+        return _head_engine(self, unet, device, list(self.parameters()) + list(self.buffers()),
+                            lambda: (conv.weight, conv.bias))
 
     def forward(self, x):
         import os
@@ -109,7 +121,6 @@ class _ScaledUnet(nn.Module):
     def __init__(self, unet: nn.Module, scale: float):
         super().__init__()
         self.unet, self.scale = unet, float(scale)
-        self._engines: Dict[torch.device, tuple] = {}
 
     def forward(self, x):
         import os
@@ -117,15 +128,8 @@ class _ScaledUnet(nn.Module):
         if os.environ.get("ANATOMIX_B200_DISABLE") == "1" or unet.engine_ineligible_reason(x) is not None \
                 or unet._anx_cfg["output_nc"] > 16:
             return unet(x) * self.scale
-        from .engine import Engine
-        stamp = tuple((t.data_ptr(), t._version) for t in list(unet.parameters()) + list(unet.buffers()))
-        eng, old = self._engines.get(x.device, (None, None))
-        if eng is None:
-            eng = Engine(unet._anx_cfg, x.device)
-        if old != stamp:
-            eng.load_state(unet.state_dict())
-            eng.set_head(torch.eye(unet._anx_cfg["output_nc"]) * self.scale, None)
-            self._engines[x.device] = (eng, stamp)
+        eng = _head_engine(self, unet, x.device, list(unet.parameters()) + list(unet.buffers()),
+                           lambda: (torch.eye(unet._anx_cfg["output_nc"]) * self.scale, None))
         return eng.forward(x)
 
 

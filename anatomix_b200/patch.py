@@ -55,7 +55,7 @@ def patch_reference(unet_cls=None):
         from anatomix.model.network import Unet as unet_cls   # the reference's (or the shim's) class
     if getattr(unet_cls, "_anx_patched", False) or hasattr(unet_cls, "engine_ineligible_reason"):
         return unet_cls
-    from .engine import ModuleBinding, ineligible_reason
+    from .engine import binding_for, ineligible_reason
     stock_forward = unet_cls.forward
 
     @functools.wraps(stock_forward)
@@ -63,14 +63,14 @@ def patch_reference(unet_cls=None):
         if os.environ.get("ANATOMIX_B200_DISABLE") != "1":
             cfg = self.__dict__.get("_anx_cfg")
             if cfg is None:
+                # a plain dict of constructor kwargs: the only thing patch mode leaves on the instance, so
+                # deepcopy / pickle / torch.save of a patched model behave as before (the engine binding is
+                # kept in anatomix_b200.engine's weakly keyed registry)
                 cfg = _cfg_from_reference_module(self)
-                binding = ModuleBinding(self, cfg)
                 self.__dict__["_anx_cfg"] = cfg
-                self.__dict__["_anx_binding"] = binding
-                self.__dict__["_engine_binding"] = lambda: binding     # what ineligible_reason asks tapped calls for
             tapping = len(layers) > 0
             if not (tapping and verbose) and ineligible_reason(self, cfg, input, layers) is None:
-                binding = self.__dict__["_anx_binding"]
+                binding = binding_for(self, cfg)
                 if tapping:       # feature taps the engine stores (network.py:475-529)
                     return binding.forward_taps(input, layers, encode_only)
                 return binding.forward(input)

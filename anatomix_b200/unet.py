@@ -161,14 +161,21 @@ class Unet(nn.Module):
             residual_connection=residual_connection, pooling=pooling,
             interp=interp, use_skip_connection=use_skip_connection,
             norm_eps=norm_eps)
-        self._anx_binding = None
 
     # ------------------------------------------------------------------ engine
     def _engine_binding(self):
-        if self._anx_binding is None:
-            from .engine import ModuleBinding
-            self._anx_binding = ModuleBinding(self, self._anx_cfg)
-        return self._anx_binding
+        """The engine binding of this module.  It lives in a weakly keyed registry next to the engine code,
+        not on the module: ``copy.deepcopy``, ``pickle`` and ``torch.save(model)`` keep working after the
+        engine has run (ctypes handles cannot be copied or pickled)."""
+        from .engine import binding_for
+        return binding_for(self, self._anx_cfg)
+
+    def invalidate_engine(self):
+        """Re-pack the engine's weights on the next forward.  Needed only after edits through ``.data``
+        (which bypass the version counters the binding watches); such edits are otherwise picked up by the
+        periodic content check (`anatomix_b200.engine.VERIFY_EVERY`)."""
+        from .engine import invalidate
+        invalidate(self)
 
     def engine_ineligible_reason(self, x, layers=()):
         """None when this call goes to the B200 engine, else why it does not

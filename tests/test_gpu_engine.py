@@ -281,7 +281,7 @@ def test_module_routes_to_engine_and_back(state_6m):
         m.model[65].weight.mul_(2.0)
         y2 = m(xc)
     assert rel_l2(y2.cpu(), 2 * y.cpu()) < 1e-2
-    assert list(m._anx_binding.engines) == [(torch.device("cuda", 0), 0)]
+    assert list(m._engine_binding().engines) == [(torch.device("cuda", 0), 0)]
 
 
 @pytest.mark.parametrize("input_nc", [2, 3, 4])

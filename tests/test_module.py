@@ -126,8 +126,30 @@ def test_import_path_shim():
     code = ("from anatomix.model.network import Unet, get_norm_layer, get_actvn_layer, ConvBlock;"
             "from anatomix.model.load_from_hf import load_from_hf, ANATOMIX_VARIANTS, _load_handling_compile, DEFAULT_REPO;"
             "import anatomix_b200.unet as u; assert Unet is u.Unet; print('ok')")
-    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "shims"), ROOT]))
+    r = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, env=env)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_repo_on_path_does_not_shadow_the_reference_package():
+    """reference installed + this repository on PYTHONPATH.  `anatomix` must stay the
+    reference's package (all of its subpackages importable as far as their own dependencies allow) and
+    `patch_reference()` must patch the reference's class."""
+    code = f"""
+import importlib.util, os, sys
+import anatomix, anatomix.model.network as net
+assert os.path.realpath(anatomix.__file__).startswith({REF!r}), anatomix.__file__
+for sub in ("anatomix.registration", "anatomix.segmentation", "anatomix.model.vit3d", "anatomix.model.load_from_hf"):
+    assert importlib.util.find_spec(sub) is not None, sub        # resolvable: nothing shadows the reference tree
+import anatomix_b200
+cls = anatomix_b200.patch_reference()
+assert cls is net.Unet and cls._anx_patched and cls.__module__ == "anatomix.model.network"
+print("ok")
+"""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, REF]))
+    r = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
