@@ -25,6 +25,9 @@ FLAG_STORE_FP16 = 2
 FLAG_STORE_BF16 = 4
 FLAG_DEPTH_HALO_INPUT = 8
 FLAG_NO_UPCONV = 16
+FLAG_NO_ROWS = 32
+PAYLOAD_F32_NCDHW = 0
+PAYLOAD_CL16 = 1
 
 # every symbol include/anatomix_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -36,6 +39,8 @@ EXPORTS = [
     "anx_engine_num_steps", "anx_engine_step_info", "anx_engine_run_steps",
     "anx_engine_forward_allgather", "anx_engine_row_layout", "anx_engine_set_head", "anx_engine_out_channels",
     "anx_engine_num_taps", "anx_engine_tap_info", "anx_engine_export_tap", "anx_avgpool3d_scale_f32", "anx_blend_window_f32", "anx_engine_set_slab", "anx_engine_step_stats",
+    "anx_engine_forward_gather", "anx_engine_forward_cl16", "anx_engine_storage_type", "anx_widen_cl16_f32",
+    "anx_push_to_peers", "anx_engine_forward_slab", "anx_engine_forward_host_ex",
 ]
 
 
@@ -45,6 +50,11 @@ class UnetDesc(C.Structure):
                 ("norm_eps", C.c_float), ("act_kind", C.c_int32), ("act_slope", C.c_float),
                 ("pool_kind", C.c_int32), ("interp_kind", C.c_int32), ("device", C.c_int32),
                 ("flags", C.c_uint32)]
+
+
+class SlabLinks(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("lower_workspace", C.c_void_p), ("upper_workspace", C.c_void_p),
+                ("flags", C.c_void_p), ("lower_flags", C.c_void_p), ("upper_flags", C.c_void_p)]
 
 
 class EngineError(RuntimeError):
@@ -102,6 +112,20 @@ def load():
     lib.anx_engine_run_steps.restype = i32
     lib.anx_engine_forward_allgather.argtypes = [vp, vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.anx_engine_forward_allgather.restype = i32
+    lib.anx_engine_forward_gather.argtypes = [vp, vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.anx_engine_forward_gather.restype = i32
+    lib.anx_engine_forward_cl16.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]
+    lib.anx_engine_forward_cl16.restype = i32
+    lib.anx_engine_storage_type.argtypes = [vp]
+    lib.anx_engine_storage_type.restype = i32
+    lib.anx_widen_cl16_f32.argtypes = [vp, vp, C.c_int64, i32, i32, i32, i32, i32, vp]
+    lib.anx_widen_cl16_f32.restype = i32
+    lib.anx_push_to_peers.argtypes = [vp, vp, C.POINTER(vp), i32, i32, sz, vp]
+    lib.anx_push_to_peers.restype = i32
+    lib.anx_engine_forward_slab.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, sz, C.POINTER(SlabLinks), vp]
+    lib.anx_engine_forward_slab.restype = i32
+    lib.anx_engine_forward_host_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.anx_engine_forward_host_ex.restype = i32
     lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_row_layout.restype = i32
     lib.anx_engine_set_head.argtypes = [vp, i32, vp, vp, i32]

@@ -15,8 +15,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc")
-# experiments: ANX_LIB_VARIANT=<tag> builds lib/libanatomix_b200_<tag>.so with the extra nvcc flags in
-# ANX_BUILD_DEFS (e.g. -DANX_EPI_WARPS=16); _lib.py loads the same variant when the variable is set
+# experiments: ANX_LIB_VARIANT=<tag> builds lib/libanatomix_b200_<tag>.so with -DANX_EXPERIMENTS (the ANX_ABLATE /
+# ANX_NO_* / ANX_ROWS / ANX_X_LEAD timing switches, which skip work and produce wrong results, exist only in
+# such builds) plus the extra nvcc flags in ANX_BUILD_DEFS (e.g. -DANX_EPI_WARPS=16); _lib.py loads the same
+# variant when the variable is set.  The product library (no variant) ignores all of those variables.
 VARIANT = os.environ.get("ANX_LIB_VARIANT", "")
 OBJ = os.path.join(PKG, "lib", "obj" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(PKG, "lib", "libanatomix_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
@@ -54,7 +56,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([nvcc, *NVCC_FLAGS, *os.environ.get("ANX_BUILD_DEFS", "").split(), "-c", src, "-o", obj],
+        defs = (["-DANX_EXPERIMENTS"] if VARIANT else []) + os.environ.get("ANX_BUILD_DEFS", "").split()
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *defs, "-c", src, "-o", obj],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -59,7 +59,7 @@ struct RowsShared {
 };
 static_assert(offsetof(RowsShared, shift) % 16 == 0, "shift must be 16-byte aligned");
 
-template <int MODE>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 or EPI_F32_HEAD
+template <int MODE>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 (also the fused gather), EPI_CL16 or EPI_F32_HEAD
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -114,11 +114,11 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                 const uint32_t st = ka % ROWS_STAGES;
                 if (lane == 0) {
                     mbar_wait(&sh->empty_a[st], ((ka / ROWS_STAGES) & 1) ^ 1, 21);
-                    if (g.ablate & 4) mbar_arrive(&sh->full_a[st]);
+                    if (ANX_ABL(g, 4)) mbar_arrive(&sh->full_a[st]);
                     else mbar_arrive_expect_tx(&sh->full_a[st], ROWS_PLANE_BYTES);
                 }
                 __syncwarp();
-                if (!(g.ablate & 4) && lane < 2 * ROWS_IN_Y) {
+                if (!(ANX_ABL(g, 4)) && lane < 2 * ROWS_IN_Y) {
                     const int grp = lane / ROWS_IN_Y, row = lane - grp * ROWS_IN_Y;
                     // padded coordinates: plane z0 + p, row y0 + row, 130 voxels from x0 (= interior x0 - 1)
                     bulk_load_1d(a_ring + (size_t)st * ROWS_PLANE_BYTES + (size_t)grp * ROWS_GROUP_BYTES +
@@ -146,7 +146,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                 for (int s = 0; s < 2; ++s) {
                     mbar_wait_warp(&sh->drained[s], ka & 1, 24);   // the slot this plane touches first is re-seeded
                     tc_fence_after();
-                    if (!(g.ablate & 1)) {
+                    if (!(ANX_ABL(g, 1))) {
 #pragma unroll
                         for (int i = 0; i < ROWS_BY + 2; ++i) {
                             const int yo_min = i - 2 > 0 ? i - 2 : 0;
@@ -304,7 +304,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) pm[i] = r == 0 ? pk[i] : max16x2(pm[i], pk[i], ep.dt);
                             }
-                            if (g.ablate & 2) continue;
+                            if (ANX_ABL(g, 2)) continue;
                             const size_t rowp = (size_t)ep.dst.pitch, plane = rowp * (Hh + 2), gstride = plane * (Dd + 2);
                             uint4 *pd = ep.dst.at(n, 0, z + 1, y + 1, x + 1);
                             *pd = q0;
@@ -317,13 +317,30 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                                 store_mirrors(pd + gstride, q1, mdz, mdy, mdx, rowp, plane);
                             }
                         } else if constexpr (MODE == EPI_F32) {
-                            if (g.ablate & 2) continue;
-                            float *po = ep.out_f32 + (size_t)n * ep.cout * vol + ((size_t)z * Hh + y) * Ww + x;
+                            if (ANX_ABL(g, 2)) continue;
+                            // fp32 NCDHW: a warp writes one 128-byte run per channel; with a fused feature
+                            // all-gather the same runs go to every rank's gather buffer over NVLink
+                            const size_t off = (size_t)(ep.sample_offset + n) * ep.cout * vol + ((size_t)z * Hh + y) * Ww + x;
+                            const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
+                            for (int pr = 0; pr < targets; ++pr) {
+                                float *po = (ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32) + off;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < ep.cout) po[(size_t)i * vol] = v[i];
+                                for (int i = 0; i < 16; ++i)
+                                    if (i < ep.cout) po[(size_t)i * vol] = v[i];
+                            }
+                        } else if constexpr (MODE == EPI_CL16) {
+                            if (ANX_ABL(g, 2)) continue;
+                            // 16-bit channels-last [N, D, H, W, 16]: 32 contiguous bytes per lane, 1 KB per warp
+                            const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
+                            const size_t off = ((((size_t)(ep.sample_offset + n) * Dd + z) * Hh + y) * Ww + x) * 2;
+                            const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
+                            for (int pr = 0; pr < targets; ++pr) {
+                                uint4 *po = reinterpret_cast<uint4 *>(ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32) + off;
+                                po[0] = q0;
+                                po[1] = q1;
+                            }
                         } else {
-                            if (g.ablate & 2) continue;
+                            if (ANX_ABL(g, 2)) continue;
                             const float *hb = sh->shift + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
                             float *po = ep.out_f32 + (size_t)n * ep.head_nc * vol + ((size_t)z * Hh + y) * Ww + x;
 #pragma unroll 2
@@ -354,7 +371,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                                     pm[i] = max16x2(pm[i], held[s][i], ep.dt);
                                     pm[i] = max16x2(pm[i], __shfl_xor_sync(0xffffffffu, pm[i], 1), ep.dt);
                                 }
-                                if (!(lane & 1) && !(g.ablate & 2))
+                                if (!(lane & 1) && !(ANX_ABL(g, 2)))
                                     store_padded_groups(ep.pool_dst, n, 0, 2, z >> 1, (y0 + s * ROWS_BY + 2 * h) >> 1, x >> 1,
                                                         make_uint4(pm[0], pm[1], pm[2], pm[3]),
                                                         make_uint4(pm[4], pm[5], pm[6], pm[7]));

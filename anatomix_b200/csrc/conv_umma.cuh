@@ -113,7 +113,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         if (lane == 0) {
             uint32_t ka = 0, kb = 0;
             if (g.b_static && blockIdx.x < g.total_tiles) {   // the one weight slab of this layer: resident for the whole launch
-                if (g.ablate & 8) {
+                if (ANX_ABL(g, 8)) {
                     mbar_arrive(&sh->full_b[0]);
                 } else {
                     mbar_arrive_expect_tx(&sh->full_b[0], g.b_stage_bytes);
@@ -125,7 +125,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                 for (int c = 0; c < g.cin_chunks; ++c) {
                     const uint32_t sa = ka % g.a_stages;
                     mbar_wait(&sh->empty_a[sa], ((ka / g.a_stages) & 1) ^ 1, 1);
-                    if (g.ablate & 4) {
+                    if (ANX_ABL(g, 4)) {
                         mbar_arrive(&sh->full_a[sa]);
                     } else {
                         mbar_arrive_expect_tx(&sh->full_a[sa], g.a_stage_bytes);
@@ -137,7 +137,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                     for (int grp = 0; grp < g.groups; ++grp) {
                         const uint32_t sb = kb % g.b_stages;
                         mbar_wait(&sh->empty_b[sb], ((kb / g.b_stages) & 1) ^ 1, 2);
-                        if (g.ablate & 8) {
+                        if (ANX_ABL(g, 8)) {
                             mbar_arrive(&sh->full_b[sb]);
                         } else {
                             mbar_arrive_expect_tx(&sh->full_b[sb], g.b_stage_bytes);
@@ -177,7 +177,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                     mbar_wait_warp(&sh->full_b[sb], g.b_static ? 0u : (kb / g.b_stages) & 1, 5);
                     tc_fence_after();
                     const uint32_t b_lo = ((smem_u32(b_ring + (size_t)sb * g.b_stage_bytes) & 0x3FFFF) >> 4) | b_lbo_bits;
-                    if (g.ablate & 1) {
+                    if (ANX_ABL(g, 1)) {
                     } else if (g.fold) {
                         for (int j = 0; j < g.bz + 2; ++j) {
                             const int lo = j - 2 > 0 ? j - 2 : 0;
@@ -186,7 +186,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                             const uint32_t dcol = acc + lo * g.ncols;
                             const uint32_t aj = a_lo + j * (HALO_Y * HALO_X);
                             const uint32_t bj = b_lo + (uint32_t)(lo - (j - 2)) * g.ncols;   // first B row, 16 B each
-                            if (g.ablate & 32) {   // timing experiment: 128-byte aligned core matrices (SBO = 128 B)
+                            if (ANX_ABL(g, 32)) {   // timing experiment: 128-byte aligned core matrices (SBO = 128 B)
                                 const uint32_t a_hi_al = (128u >> 4) | (1u << 14);
                                 const uint32_t aj_al = a_lo + j * 176;
 #pragma unroll
@@ -194,7 +194,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                                     umma_bf16_warp(dcol, make_desc(a_hi_al, aj_al + t * 8), make_desc(b_hi, bj + t * b_tap), idesc);
                                 continue;
                             }
-                            if (g.ablate & 16) {   // timing experiment: every tap reads the aligned brick origin
+                            if (ANX_ABL(g, 16)) {   // timing experiment: every tap reads the aligned brick origin
 #pragma unroll
                                 for (int t = 0; t < 9; ++t)
                                     umma_bf16_warp(dcol, make_desc(a_hi, a_lo), make_desc(b_hi, bj + t * b_tap), idesc);
@@ -210,6 +210,15 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         for (int b = 0; b < g.bz; ++b) {
                             const uint32_t dcol = acc + b * g.ncols;
                             const uint32_t aj = a_lo + (b + grp) * (HALO_Y * HALO_X);   // grp = kz = dz + 1
+                            if (g.trim) {      // structurally sparse B: only the columns this tap can reach
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) {
+                                    const uint32_t lo = 16u * g.trim_lo[grp * 9 + t], nn = 16u * g.trim_n[grp * 9 + t];
+                                    umma_bf16_warp(dcol + lo, make_desc(a_hi, aj + (t / 3) * HALO_X + (t % 3)),
+                                                   make_desc(b_hi, b_lo + t * b_tap + lo), idesc_m128(nn, g.dt));
+                                }
+                                continue;
+                            }
 #pragma unroll
                             for (int t = 0; t < 9; ++t)
                                 umma_bf16_warp(dcol, make_desc(a_hi, aj + (t / 3) * HALO_X + (t % 3)),
@@ -239,7 +248,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
             et.n = t.n; et.z0 = t.z0; et.y = t.y0 + ly; et.x = t.x0 + lx;
             et.chan0 = t.split * g.ncols;
             et.in_xy = (et.y < g.H) && (et.x < g.W);
-            et.store = !(g.ablate & 2);
+            et.store = !(ANX_ABL(g, 2));
             return et;
         };
         // seed every accumulator stage for the first tile that will use it

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/anatomix_b200.h"
+#include "comm_kernels.cuh"
 #include "conv_rows.cuh"
 #include "conv_umma.cuh"
 #include "simt_kernels.cuh"
@@ -56,6 +57,16 @@ inline uint16_t f32_to_f16_rne(float f) {
     return (uint16_t)(sign | h);
 }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Environment switches for A/B timing experiments: read only by -DANX_EXPERIMENTS builds (see layout.cuh).
+inline const char *exp_env(const char *name) {
+#ifdef ANX_EXPERIMENTS
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -131,9 +142,10 @@ struct TapSite {
     int last_step;                      // the tensor is complete once steps [0, last_step] have run
 };
 
-struct GatherArgs {           // fused all-gather destinations of the final conv (one forward call)
-    float *peers[8] = {nullptr};
+struct GatherArgs {           // where and how the final conv stores (one forward call)
+    float *peers[8] = {nullptr};     // fused feature all-gather: every rank's gather buffer (n_peers = 0: `out` only)
     int n_peers = 0, sample_offset = 0;
+    int payload = ANX_PAYLOAD_F32_NCDHW;
 };
 
 struct ShapePlan {            // everything that depends on (N, D, H, W, workspace)
@@ -172,6 +184,13 @@ struct anx_engine {
     std::mutex host_mu;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in[8] = {nullptr}, ev_out[8] = {nullptr};
+    // copy-engine push of the feature all-gather (anx_push_to_peers): one stream per destination
+    cudaStream_t push_stream[8] = {nullptr};
+    cudaEvent_t ev_push_fork = nullptr, ev_push_done[8] = {nullptr};
+    // depth-slab forward (anx_engine_forward_slab): exchange counter (same on every rank) and the ticket the
+    // halo kernel's CTAs draw
+    uint32_t slab_seq = 0;
+    unsigned int *d_ticket = nullptr;
     mutable std::string last_error;
 
     anx_status fail(anx_status st, const char *fmt, ...) const {
@@ -259,7 +278,7 @@ void build_program(anx_engine *e) {
         add_conv(e, mi, i == 0 ? g : width[i - 1], width[i], i, false, false, cur, t, 0);
         add_conv(e, mi, width[i], width[i], i, false, false, t, cat[i], 0);
         int p = add_buffer(e, i + 1, width[i]);
-        if (!(d.flags & ANX_FLAG_FORCE_SIMT) && d.norm_kind != ANX_NORM_INSTANCE && !getenv("ANX_NO_POOL_FUSION"))
+        if (!(d.flags & ANX_FLAG_FORCE_SIMT) && d.norm_kind != ANX_NORM_INSTANCE && !exp_env("ANX_NO_POOL_FUSION"))
             e->convs.back().pool_dst_buf = p;     // epilogue-fused when the tile shape allows (see make_geom)
         Step s{};
         s.kind = STEP_POOL;
@@ -289,7 +308,7 @@ void build_program(anx_engine *e) {
     // depth-to-space as 16-bit partial sums, which then seed the accumulators of the w -> w skip conv.
     const bool use_upconv = d.interp_kind == ANX_INTERP_NEAREST && d.norm_kind != ANX_NORM_INSTANCE &&
                             !(d.flags & (ANX_FLAG_FORCE_SIMT | ANX_FLAG_NO_UPCONV)) && width[0] == 16 &&
-                            !getenv("ANX_NO_UPCONV");   // the seeded skip conv handles one 16-channel chunk
+                            !exp_env("ANX_NO_UPCONV");   // the seeded skip conv handles one 16-channel chunk
     std::vector<std::pair<int, int>> pairs;
     for (int l = nd - 1; l >= 0; --l) {
         if (use_upconv && l == 0) {
@@ -409,11 +428,11 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.in_group_offset = 0;
     // Single-slab layers (one 16-channel chunk, folded dz, no channel split: the 16 -> 16 convs) use the
     // same B image for every tile: it is loaded once per CTA and stays in shared memory.
-    g.b_static = (c.fold && g.cin_chunks == 1 && c.n_splits == 1 && !getenv("ANX_NO_BSTATIC")) ? 1 : 0;
+    g.b_static = (c.fold && g.cin_chunks == 1 && c.n_splits == 1 && !exp_env("ANX_NO_BSTATIC")) ? 1 : 0;
     // output planes per tile: as many as TMEM double buffering allows, at most 8 -- or 16 for the thin
     // single-slab layers, whose MMA count per output plane is 9 * (bz + 2) / bz (all of TMEM, two A stages)
     int bz = std::max(1, std::min(8, 256 / g.ncols));
-    if (g.b_static && g.ncols == 16 && D >= 16 && !getenv("ANX_NO_BZ16")) bz = 16;
+    if (g.b_static && g.ncols == 16 && D >= 16 && !exp_env("ANX_NO_BZ16")) bz = 16;
     g.acc_stages = 2;
     bz = std::min(bz, D);
     g.bz = bz;
@@ -440,9 +459,26 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.b_stages = (int)std::min<size_t>(MAX_B_STAGES, left / g.b_stage_bytes);
     g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
     if (g.b_static) g.b_stages = std::min(g.b_stages, 1);
-    if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
+    if (const char *ab = exp_env("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
     g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
                               sizeof(UmmaShared));
+    // Low-resolution half of a decoder conv: column (parity p = a*4 + b*2 + c, channel) of low-resolution tap
+    // offset o in {-1, 0, +1} along an axis is non-zero only for parity 0 (o = -1), both (o = 0) or parity 1
+    // (o = +1) of that axis (see anx_engine_set_conv).  Each tap's MMA covers just the span of its parities.
+    if (c.d2s_cout > 0 && !c.fold && c.n_splits == 1 && c.d2s_cout % 16 == 0 && !exp_env("ANX_NO_TRIM")) {
+        g.trim = 1;
+        const int blocks = c.d2s_cout / 16;        // 16-column blocks per parity
+        auto span = [](int o, int &lo, int &hi) { lo = o == 2 ? 1 : 0; hi = o == 0 ? 0 : 1; };   // o = offset + 1
+        for (int kz = 0; kz < 3; ++kz)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    int al, ah, bl, bh, cl, ch;
+                    span(kz, al, ah); span(ky, bl, bh); span(kx, cl, ch);
+                    const int pmin = al * 4 + bl * 2 + cl, pmax = ah * 4 + bh * 2 + ch;
+                    g.trim_lo[kz * 9 + ky * 3 + kx] = (uint8_t)(pmin * blocks);
+                    g.trim_n[kz * 9 + ky * 3 + kx] = (uint8_t)((pmax - pmin + 1) * blocks);
+                }
+    }
     return g;
 }
 
@@ -545,6 +581,7 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         for (int i = 0; i < ga->n_peers; ++i) ep.out_peers[i] = ga->peers[i];
         ep.n_peers = ga->n_peers;
         ep.sample_offset = ga->sample_offset;
+        ep.cl16 = ga->payload == ANX_PAYLOAD_CL16 ? 1 : 0;
     }
     ep.cout = c.cout;
     ep.bias = c.d_bias;
@@ -589,7 +626,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         Epilogue ep = make_epilogue(e, p, c, out);
         const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
         if (!force_simt && c.d_wstem && p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
-            !getenv("ANX_SIMT_STEM")) {
+            !exp_env("ANX_SIMT_STEM")) {
             // tensor-core stem: per-call tensor map over the caller's fp32 input
             EncodeTiledFn encode = load_encode_tiled();
             StemGeom g{};
@@ -597,14 +634,14 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             g.ncols = c.ncols;
             g.kq = (9 * c.cin + 15) / 16;
             g.bz = std::min(std::max(1, std::min(8, 256 / c.ncols)), p.D);
-            if (c.ncols == 16 && c.cin == 1 && p.D >= 16 && !getenv("ANX_NO_BZ16")) g.bz = 16;   // all of TMEM: 18 input planes per 16
+            if (c.ncols == 16 && c.cin == 1 && p.D >= 16 && !exp_env("ANX_NO_BZ16")) g.bz = 16;   // all of TMEM: 18 input planes per 16
             g.acc_stages = 2;
             int cols = 32;
             while (cols < g.acc_stages * g.bz * g.ncols) cols *= 2;
             g.tmem_cols = cols;
             g.z_halo = zh0;
-            if (const char *ds = getenv("ANX_STEM_SHIFT")) g.dbg_shift = atoi(ds);
-            if (const char *ab = getenv("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
+            if (const char *ds = exp_env("ANX_STEM_SHIFT")) g.dbg_shift = atoi(ds);
+            if (const char *ab = exp_env("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
             g.tiles_x = (p.W + TILE_X - 1) / TILE_X;
             g.tiles_y = (p.H + TILE_Y - 1) / TILE_Y;
             g.tiles_z = (p.D + g.bz - 1) / g.bz;
@@ -656,11 +693,13 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const ConvLayer &c = e->convs[s.conv];
         const ConvGeom &g = p.geoms[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
-        if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0))
-            return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path without a fused gather");
+        if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0 || ep.cl16))
+            return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path with the plain fp32 output");
+        if (ep.cl16 && (force_simt || (c.cout & 7)))
+            return e->fail(ANX_ERR_UNSUPPORTED, "the 16-bit channels-last output needs the tensor-core path and output_nc % 8 == 0");
         if (!force_simt && e->use_rows && c.d_wrows && !(g.fuse_pool && ep.pool_kind != 0) && !ep.stats && !ep.d2s_cout &&
             !((e->use_rows & 2) && (g.fuse_pool || ep.seed_on)) &&      // ANX_ROWS=3: plain / fp32 variants only
-            ep.n_peers == 0 && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
+            !(ep.cl16 && c.cout != 16) && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
             RowsGeom rg{};
             rg.N = g.N; rg.D = g.D; rg.H = g.H; rg.W = g.W;
             rg.zs = 16;
@@ -674,7 +713,11 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const int grid = std::min(rg.total_units, e->num_sms);
             const uint8_t *wr = (const uint8_t *)c.d_wrows;
 #define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep)
-            if (ep.mode == OUT_NCDHW_F32) { if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD); else ANX_ROWS_LAUNCH(EPI_F32); }
+            if (ep.mode == OUT_NCDHW_F32) {
+                if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD);
+                else if (ep.cl16) ANX_ROWS_LAUNCH(EPI_CL16);
+                else ANX_ROWS_LAUNCH(EPI_F32);       // also the fused gather (peer loop inside)
+            }
             else if (ep.seed_on) ANX_ROWS_LAUNCH(EPI_SEEDED);
             else if (g.fuse_pool) ANX_ROWS_LAUNCH(EPI_POOL);
             else ANX_ROWS_LAUNCH(EPI_PADDED);
@@ -691,7 +734,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const uint8_t *wp_ = (const uint8_t *)c.d_wpack;
 #define ANX_CONV(MODE_) conv3_umma_kernel<MODE_><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g, wp_, ep)
             if (ep.mode == OUT_NCDHW_F32) {
-                if (ep.n_peers > 0) ANX_CONV(EPI_F32_PEERS);
+                if (ep.cl16) ANX_CONV(EPI_CL16);
+                else if (ep.n_peers > 0) ANX_CONV(EPI_F32_PEERS);
                 else if (ep.head_nc > 0) ANX_CONV(EPI_F32_HEAD);
                 else ANX_CONV(EPI_F32);
             }
@@ -814,19 +858,21 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (desc->flags & ANX_FLAG_STORE_BF16) e->dt = DT_BF16;
     e->num_sms = prop.multiProcessorCount;
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
-    if (const char *xl = getenv("ANX_X_LEAD")) e->x_lead = atoi(xl);
-    if (const char *rw = getenv("ANX_ROWS")) e->use_rows = atoi(rw);
+    if (const char *xl = exp_env("ANX_X_LEAD")) e->x_lead = atoi(xl);
+    if (desc->flags & ANX_FLAG_NO_ROWS) e->use_rows = 0;
+    if (const char *rw = exp_env("ANX_ROWS")) e->use_rows = atoi(rw);
     build_program(e);
     build_taps(e);
     for (auto &c : e->convs) {
-        c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !getenv("ANX_NOFOLD")) ? 1 : 0;
+        c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !exp_env("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
     }
     cudaError_t err = cudaSuccess;
 #define ANX_SMEM(K_) if (err == cudaSuccess) err = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem)
     ANX_SMEM(conv3_umma_kernel<EPI_PADDED>); ANX_SMEM(conv3_umma_kernel<EPI_POOL>); ANX_SMEM(conv3_umma_kernel<EPI_D2S>);
     ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
-    ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>);
+    ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>); ANX_SMEM(conv3_umma_kernel<EPI_CL16>);
+    ANX_SMEM(conv3_rows_kernel<EPI_CL16>);
     ANX_SMEM(conv3_rows_kernel<EPI_PADDED>); ANX_SMEM(conv3_rows_kernel<EPI_F32>); ANX_SMEM(conv3_rows_kernel<EPI_F32_HEAD>);
     ANX_SMEM(conv3_rows_kernel<EPI_SEEDED>); ANX_SMEM(conv3_rows_kernel<EPI_POOL>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
@@ -853,6 +899,12 @@ void anx_engine_destroy(anx_engine *e) {
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
     if (e->d_head) cudaFree(e->d_head);
+    if (e->d_ticket) cudaFree(e->d_ticket);
+    if (e->ev_push_fork) cudaEventDestroy(e->ev_push_fork);
+    for (int i = 0; i < 8; ++i) {
+        if (e->push_stream[i]) cudaStreamDestroy(e->push_stream[i]);
+        if (e->ev_push_done[i]) cudaEventDestroy(e->ev_push_done[i]);
+    }
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
@@ -1145,12 +1197,13 @@ anx_status anx_engine_run_steps(anx_engine *e, const float *in, float *out, int3
     return ANX_OK;
 }
 
-anx_status anx_engine_forward_allgather(anx_engine *e, const float *in, float *const *out_peers, int32_t world,
-                                        int32_t rank, int32_t n, int32_t d, int32_t h, int32_t w, void *workspace,
-                                        size_t ws_bytes, void *stream) {
+anx_status anx_engine_forward_gather(anx_engine *e, const float *in, void *const *out_peers, int32_t world,
+                                     int32_t rank, int32_t payload, int32_t n, int32_t d, int32_t h, int32_t w,
+                                     void *workspace, size_t ws_bytes, void *stream) {
     if (!e) return ANX_ERR_BAD_ARG;
     if (!out_peers || world < 1 || world > 8 || rank < 0 || rank >= world)
         return e->fail(ANX_ERR_BAD_ARG, "bad peer list (world %d, rank %d; at most 8 peers)", world, rank);
+    if (payload != ANX_PAYLOAD_F32_NCDHW && payload != ANX_PAYLOAD_CL16) return e->fail(ANX_ERR_BAD_ARG, "bad payload kind");
     for (int i = 0; i < world; ++i)
         if (!out_peers[i]) return e->fail(ANX_ERR_BAD_ARG, "null gather buffer for peer %d", i);
     anx_status st = check_forward_args(e, in, out_peers[rank], n, d, h, w, workspace, ws_bytes);
@@ -1160,15 +1213,147 @@ anx_status anx_engine_forward_allgather(anx_engine *e, const float *in, float *c
     st = get_plan(e, n, d, h, w, workspace, p);
     if (st != ANX_OK) return st;
     GatherArgs ga;
-    for (int i = 0; i < world; ++i) ga.peers[i] = out_peers[i];
+    for (int i = 0; i < world; ++i) ga.peers[i] = static_cast<float *>(out_peers[i]);
     ga.n_peers = world;
     ga.sample_offset = rank * n;
+    ga.payload = payload;
     if (p->stats_bytes)
         ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes,
                                     static_cast<cudaStream_t>(stream)));
     for (auto &s : e->steps) {
-        st = launch_step(e, *p, s, in, out_peers[rank], static_cast<cudaStream_t>(stream), &ga);
+        st = launch_step(e, *p, s, in, static_cast<float *>(out_peers[rank]), static_cast<cudaStream_t>(stream), &ga);
         if (st != ANX_OK) return st;
+    }
+    return ANX_OK;
+}
+
+anx_status anx_engine_forward_allgather(anx_engine *e, const float *in, float *const *out_peers, int32_t world,
+                                        int32_t rank, int32_t n, int32_t d, int32_t h, int32_t w, void *workspace,
+                                        size_t ws_bytes, void *stream) {
+    return anx_engine_forward_gather(e, in, reinterpret_cast<void *const *>(out_peers), world, rank,
+                                     ANX_PAYLOAD_F32_NCDHW, n, d, h, w, workspace, ws_bytes, stream);
+}
+
+anx_status anx_engine_forward_cl16(anx_engine *e, const float *in, void *out_cl16, int32_t n, int32_t d, int32_t h,
+                                   int32_t w, void *workspace, size_t ws_bytes, void *stream) {
+    void *one[1] = {out_cl16};
+    return anx_engine_forward_gather(e, in, one, 1, 0, ANX_PAYLOAD_CL16, n, d, h, w, workspace, ws_bytes, stream);
+}
+
+int32_t anx_engine_storage_type(const anx_engine *e) { return e ? e->dt : -1; }
+
+anx_status anx_widen_cl16_f32(const void *src_cl16, float *dst_ncdhw, int64_t n, int32_t channels, int32_t d,
+                              int32_t h, int32_t w, int32_t storage_type, void *stream) {
+    if (!src_cl16 || !dst_ncdhw || n < 1 || channels < 8 || (channels & 7) || d < 1 || h < 1 || w < 1 ||
+        (storage_type != DT_BF16 && storage_type != DT_FP16))
+        return ANX_ERR_BAD_ARG;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t vol = (size_t)d * h * w;
+    widen_cl16_kernel<<<grid_for((size_t)n * vol, 256, sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4 *>(src_cl16), dst_ncdhw, (size_t)n, vol, channels, storage_type);
+    return cudaGetLastError() == cudaSuccess ? ANX_OK : ANX_ERR_CUDA;
+}
+
+anx_status anx_push_to_peers(anx_engine *e, const void *src, void *const *peer_dst, int32_t world, int32_t rank,
+                             size_t bytes, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (!src || !peer_dst || world < 1 || world > 8 || rank < 0 || rank >= world)
+        return e->fail(ANX_ERR_BAD_ARG, "bad peer list (world %d, rank %d; at most 8 peers)", world, rank);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!e->ev_push_fork) {
+        ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_push_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) {
+            ANX_CUDA(e, cudaStreamCreateWithFlags(&e->push_stream[i], cudaStreamNonBlocking));
+            ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_push_done[i], cudaEventDisableTiming));
+        }
+    }
+    // one copy per destination, each on its own stream so the copy engines drive all NVLink ports at
+    // once; `stream` continues when the last copy has landed
+    ANX_CUDA(e, cudaEventRecord(e->ev_push_fork, st));
+    for (int k = 1; k < world; ++k) {
+        const int r = (rank + k) % world;           // staggered start: rank i begins with peer i + 1
+        if (!peer_dst[r]) return e->fail(ANX_ERR_BAD_ARG, "null destination for peer %d", r);
+        ANX_CUDA(e, cudaStreamWaitEvent(e->push_stream[r], e->ev_push_fork, 0));
+        ANX_CUDA(e, cudaMemcpyAsync(peer_dst[r], src, bytes, cudaMemcpyDeviceToDevice, e->push_stream[r]));
+        ANX_CUDA(e, cudaEventRecord(e->ev_push_done[r], e->push_stream[r]));
+        ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_push_done[r], 0));
+    }
+    return ANX_OK;
+}
+
+anx_status anx_engine_forward_slab(anx_engine *e, const float *in, float *out, int32_t n, int32_t d, int32_t h,
+                                   int32_t w, void *workspace, size_t ws_bytes, const anx_slab_links *links,
+                                   void *stream) {
+    anx_status st = check_forward_args(e, in, out, n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    if (!links || links->struct_size != sizeof(anx_slab_links) || !links->flags)
+        return e->fail(ANX_ERR_BAD_ARG, "bad slab links");
+    if ((links->lower_workspace != nullptr) != (e->slab_lower != 0) || (links->upper_workspace != nullptr) != (e->slab_upper != 0) ||
+        (links->lower_workspace && !links->lower_flags) || (links->upper_workspace && !links->upper_flags))
+        return e->fail(ANX_ERR_BAD_ARG, "slab links do not match anx_engine_set_slab (lower %d, upper %d)", e->slab_lower,
+                       e->slab_upper);
+    for (auto &c : e->convs)
+        if (c.inorm)
+            return e->fail(ANX_ERR_UNSUPPORTED, "InstanceNorm networks need whole-volume statistics between launches: "
+                                                "use anx_engine_run_steps / anx_engine_step_stats");
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    if (!e->d_ticket) {
+        ANX_CUDA(e, cudaMalloc(&e->d_ticket, sizeof(unsigned int)));
+        ANX_CUDA(e, cudaMemset(e->d_ticket, 0, sizeof(unsigned int)));
+    }
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    // One launch per exchange: push my two boundary planes of the tensor into the neighbours' shells,
+    // publish the sequence number, wait for theirs.  groups = 0: handshake only (start of a forward: the
+    // neighbours have finished the previous one, so their shells may be overwritten).
+    auto exchange = [&](int buf, int goff, int groups) -> anx_status {
+        HaloArgs a{};
+        size_t off_bytes = 0;
+        if (groups > 0) {
+            const ActView v = view_of(e, *p, buf, goff);
+            a.plane = (size_t)(v.H + 2) * v.pitch;
+            a.group_stride = (size_t)(v.D + 2) * a.plane;
+            a.sample_stride = (size_t)e->bufs[buf].groups * a.group_stride;
+            a.D = v.D;
+            off_bytes = p->buf_offset[buf] + (size_t)goff * a.group_stride * 16;
+        }
+        a.src = reinterpret_cast<const uint4 *>(static_cast<char *>(workspace) + off_bytes);
+        a.lower = links->lower_workspace ? reinterpret_cast<uint4 *>(static_cast<char *>(links->lower_workspace) + off_bytes) : nullptr;
+        a.upper = links->upper_workspace ? reinterpret_cast<uint4 *>(static_cast<char *>(links->upper_workspace) + off_bytes) : nullptr;
+        a.groups = groups;
+        a.N = n;
+        a.my_flags = links->flags;
+        a.lower_flag = links->lower_workspace ? links->lower_flags + 1 : nullptr;
+        a.upper_flag = links->upper_workspace ? links->upper_flags + 0 : nullptr;
+        a.seq = ++e->slab_seq;
+        a.ticket = e->d_ticket;
+        const size_t per_dir = (size_t)n * groups * a.plane;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->num_sms, (per_dir + 1023) / 1024));
+        halo_exchange_kernel<<<grid, 256, 0, cs>>>(a);
+        ANX_CUDA(e, cudaGetLastError());
+        return ANX_OK;
+    };
+    st = exchange(0, 0, 0);
+    if (st != ANX_OK) return st;
+    for (auto &s : e->steps) {
+        st = launch_step(e, *p, s, in, out, cs);
+        if (st != ANX_OK) return st;
+        int buf = -1, goff = 0, groups = 0;
+        if (s.kind == STEP_STEM || s.kind == STEP_CONV) {
+            const ConvLayer &c = e->convs[s.conv];
+            if (!c.is_final && !c.d2s_cout) { buf = c.dst_buf; goff = c.dst_group_offset; groups = c.cout / 8; }
+        } else if (s.kind == STEP_POOL || s.kind == STEP_UP) {
+            buf = s.dst_buf; goff = s.dst_group_offset; groups = s.groups;
+        }
+        if (buf >= 0 && (e->slab_lower || e->slab_upper)) {
+            st = exchange(buf, goff, groups);
+            if (st != ANX_OK) return st;
+        }
     }
     return ANX_OK;
 }
@@ -1176,7 +1361,16 @@ anx_status anx_engine_forward_allgather(anx_engine *e, const float *in, float *c
 anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *out_host, int32_t n, int32_t d,
                                    int32_t h, int32_t w, float *dev_in, float *dev_out, void *workspace,
                                    size_t ws_bytes, void *stream) {
+    return anx_engine_forward_host_ex(e, in_host, out_host, ANX_PAYLOAD_F32_NCDHW, n, d, h, w, dev_in, dev_out,
+                                      workspace, ws_bytes, stream);
+}
+
+anx_status anx_engine_forward_host_ex(anx_engine *e, const float *in_host, void *out_host_v, int32_t payload,
+                                      int32_t n, int32_t d, int32_t h, int32_t w, float *dev_in, void *dev_out_v,
+                                      void *workspace, size_t ws_bytes, void *stream) {
     if (!e) return ANX_ERR_BAD_ARG;
+    if (payload != ANX_PAYLOAD_F32_NCDHW && payload != ANX_PAYLOAD_CL16) return e->fail(ANX_ERR_BAD_ARG, "bad payload kind");
+    char *out_host = static_cast<char *>(out_host_v), *dev_out = static_cast<char *>(dev_out_v);
     if (!in_host || !out_host || !dev_in || !dev_out) return e->fail(ANX_ERR_BAD_ARG, "null buffer");
     if (!shape_ok(e, n, d, h, w)) return e->fail(ANX_ERR_BAD_SHAPE, "bad shape for the host-buffer forward");
     std::lock_guard<std::mutex> lock(e->host_mu);
@@ -1196,8 +1390,9 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
     // chunk i-1 run on their own streams while chunk i computes on the caller's stream.  The
     // download (output_nc/input_nc times larger than the upload) is what bounds the call.
     const int chunks = std::min(n, 4);
+    // bytes per sample of the output in the chosen payload
     const size_t in_vol = (size_t)d * h * w * e->desc.input_nc,
-                 out_vol = (size_t)d * h * w * anx_engine_out_channels(e);
+                 out_vol = (size_t)d * h * w * anx_engine_out_channels(e) * (payload == ANX_PAYLOAD_CL16 ? 2 : 4);
     ANX_CUDA(e, cudaEventRecord(e->ev_fork, st));
     ANX_CUDA(e, cudaStreamWaitEvent(e->h2d_stream, e->ev_fork, 0));
     ANX_CUDA(e, cudaStreamWaitEvent(e->d2h_stream, e->ev_fork, 0));
@@ -1208,12 +1403,14 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
                                     cudaMemcpyHostToDevice, e->h2d_stream));
         ANX_CUDA(e, cudaEventRecord(e->ev_in[i], e->h2d_stream));
         ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_in[i], 0));
-        anx_status r = anx_engine_forward(e, dev_in + lo * in_vol, dev_out + lo * out_vol, cnt, d, h, w, workspace,
-                                          ws_bytes, stream);
+        anx_status r = payload == ANX_PAYLOAD_CL16
+            ? anx_engine_forward_cl16(e, dev_in + lo * in_vol, dev_out + lo * out_vol, cnt, d, h, w, workspace, ws_bytes, stream)
+            : anx_engine_forward(e, dev_in + lo * in_vol, reinterpret_cast<float *>(dev_out + lo * out_vol), cnt, d, h, w,
+                                 workspace, ws_bytes, stream);
         if (r != ANX_OK) return r;
         ANX_CUDA(e, cudaEventRecord(e->ev_out[i], st));
         ANX_CUDA(e, cudaStreamWaitEvent(e->d2h_stream, e->ev_out[i], 0));
-        ANX_CUDA(e, cudaMemcpyAsync(out_host + lo * out_vol, dev_out + lo * out_vol, cnt * out_vol * sizeof(float),
+        ANX_CUDA(e, cudaMemcpyAsync(out_host + lo * out_vol, dev_out + lo * out_vol, cnt * out_vol,
                                     cudaMemcpyDeviceToHost, e->d2h_stream));
         lo += cnt;
     }

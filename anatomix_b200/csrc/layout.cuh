@@ -30,6 +30,15 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+// Timing experiments (ablation bits in *Geom::ablate, ANX_* environment switches in engine.cu) exist only in
+// builds made with -DANX_EXPERIMENTS (ANX_LIB_VARIANT builds, anatomix_b200/build.py): they make launches
+// skip work and return WRONG results, so the product library compiles them out.
+#ifdef ANX_EXPERIMENTS
+#define ANX_ABL(g, bit) (((g).ablate & (bit)) != 0)
+#else
+#define ANX_ABL(g, bit) false
+#endif
+
 namespace anx {
 
 // Row geometry of a padded planar buffer of interior width W for a given lead (host side picks the lead).
@@ -80,6 +89,9 @@ struct Epilogue {
     float *out_peers[8];
     int n_peers;
     int sample_offset;
+    // OUT_NCDHW_F32 only: 1 = store the network output as 16-bit channels-last [N, D, H, W, cout] (type `dt`) instead
+    // of fp32 NCDHW -- the compact payload of the feature all-gather and of the host download.
+    int cl16;
     // Fused 2x2x2 pooling (tensor-core kernel only): besides the full-resolution store, the epilogue
     // reduces each 2x2x2 block (z pair in registers, y / x pairs by warp shuffles) and writes the
     // pooled tensor with its shell.  pool_kind: -1 off, 0 max, 1 mean.
@@ -134,6 +146,12 @@ struct ConvGeom {
     int b_static;           // 1: one B slab serves every tile; loaded once per CTA, never recycled
     uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load,
                             // 16 every tap reads the brick origin, 32 128-byte aligned core matrices (results are wrong)
+    // Column trimming (unfolded layers whose packed weights are structurally sparse: the low-resolution half of a
+    // decoder conv, engine.cu "upconv"): tap (dz group, dy*3+dx) only touches output columns
+    // [trim_lo, trim_lo + trim_n) -- the other columns of its B tile are zeros -- so its MMA is issued with N = trim_n
+    // on that column range.  trim = 0: every tap covers all ncols columns.
+    int trim;
+    uint8_t trim_lo[27], trim_n[27];   // in units of 16 columns
 };
 
 }   // namespace anx

@@ -136,7 +136,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 const int ty = r / g.tiles_x, tx = r - ty * g.tiles_x;
                 const uint32_t s = k % NB;
                 mbar_wait(&sh->empty_brick[s], ((k / NB) & 1) ^ 1, 11);
-                if (g.ablate & 8) { mbar_arrive(&sh->full_brick[s]); continue; }
+                if (ANX_ABL(g, 8)) { mbar_arrive(&sh->full_brick[s]); continue; }
                 mbar_arrive_expect_tx(&sh->full_brick[s], g.brick_bytes);
                 // box {16 x, 18 y, bz+2 z, cin}; planes of (n, c) are consecutive along dim 3
                 tma_load_4d(bricks + s * brick_stride, &tmap_in, &sh->full_brick[s], tx * TILE_X - STEM_X_LEAD + g.dbg_shift,
@@ -171,13 +171,13 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
                 const uint32_t al = ah + (g.a_tile_bytes >> 4);
 #pragma unroll
                 for (int kc = 0; kc < KQ; ++kc) {
-                    if (g.ablate & 1) break;
+                    if (ANX_ABL(g, 1)) break;
                     const uint32_t ao = kc * (2 * 128), bo = kc * (2 * R) + row0;   // 16 B units per K chunk of 16
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (ah + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (al + ao) | a_lbo), make_desc(a_hi_bits, (bh + bo) | b_lbo), idesc);
                     umma_bf16_warp(dcol, make_desc(a_hi_bits, (ah + ao) | a_lbo), make_desc(a_hi_bits, (bl + bo) | b_lbo), idesc);
                 }
-                if (g.ablate & 16) {          // timing experiment (no MMAs in flight): plain arrive instead of tcgen05.commit
+                if (ANX_ABL(g, 16)) {          // timing experiment (no MMAs in flight): plain arrive instead of tcgen05.commit
                     if (lane == 0) mbar_arrive(&sh->empty_a[sa]);
                     __syncwarp();
                 } else {
@@ -219,7 +219,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             for (int j = 0; j < planes; ++j, ++ka) {
                 if (ka % STEM_BUILD_GROUPS != group) continue;
                 const uint32_t sa = ka % STEM_A_SLOTS;
-                if (g.ablate & 4) {
+                if (ANX_ABL(g, 4)) {
                     mbar_wait(&sh->empty_a[sa], ((ka / STEM_A_SLOTS) & 1) ^ 1, 16);
                     mbar_arrive(&sh->full_a[sa]);
                     continue;
@@ -285,7 +285,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             et.n = n; et.z0 = tz * g.bz; et.y = ty * TILE_Y + ly; et.x = tx * TILE_X + lx;
             et.chan0 = 0;
             et.in_xy = (et.y < g.H) && (et.x < g.W);
-            et.store = !(g.ablate & 2);
+            et.store = !(ANX_ABL(g, 2));
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
             umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);

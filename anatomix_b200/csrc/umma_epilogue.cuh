@@ -63,7 +63,8 @@ enum EpiMode : int {
     EPI_F32 = 4,         // fp32 NCDHW network output
     EPI_F32_PEERS = 5,   // ... into every peer's gather buffer
     EPI_SEEDED = 6,      // padded store, accumulators re-seeded from stored partial sums
-    EPI_F32_HEAD = 7     // fp32 NCDHW output of a linear head applied to the conv's 16 channels
+    EPI_F32_HEAD = 7,    // fp32 NCDHW output of a linear head applied to the conv's 16 channels
+    EPI_CL16 = 8         // 16-bit channels-last [N, D, H, W, C] network output (into every peer's buffer when gathering)
 };
 constexpr int HEAD_SMEM_OFFSET = 32;   // floats behind the channel shift in shared memory where the head lives
 
@@ -77,7 +78,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     const size_t gstride = (size_t)(Dd + 2) * plane;
     const size_t vol = (size_t)Dd * Hh * Ww;
     constexpr bool SEEDED = MODE == EPI_SEEDED;
-    constexpr bool PADDED = MODE != EPI_F32 && MODE != EPI_F32_PEERS && MODE != EPI_F32_HEAD;
+    constexpr bool PADDED = MODE != EPI_F32 && MODE != EPI_F32_PEERS && MODE != EPI_F32_HEAD && MODE != EPI_CL16;
     const bool big = (Dd >= 4) & (Hh >= 4) & (Ww >= 4);         // else: generic mirror loops
     const int rep = ep.dst.shell_rep;
     const int mdx = mirror_delta(t.x, Ww, rep), mdy = mirror_delta(t.y, Hh, rep);
@@ -86,7 +87,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     float *fbase = nullptr;
     if constexpr (PADDED)
         pbase = ep.dst.at(t.n, t.chan0 >> 3, t.z0 + 1, t.y + 1, t.x + 1);
-    else
+    else if constexpr (MODE != EPI_CL16)
         fbase = ep.out_f32 + ((size_t)t.n * ep.cout + t.chan0) * vol + ((size_t)t.z0 * Hh + t.y) * Ww + t.x;
     const int chunks = ncols >> 4;
     for (int cb = 0; cb < chunks; ++cb) {
@@ -259,6 +260,17 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (c0 + i < ep.cout) o[(size_t)i * vol] = v[i];
+                } else if constexpr (MODE == EPI_CL16) {
+                    // 16-bit channels-last: a voxel's channels are contiguous (32 bytes per 16-channel chunk)
+                    const uint4 q0 = pack_x8(v, ep.dt), q1 = pack_x8(v + 8, ep.dt);
+                    const size_t cg = (size_t)(ep.cout >> 3);       // 8-channel groups per voxel
+                    const size_t off = ((((size_t)(ep.sample_offset + t.n) * Dd + z) * Hh + t.y) * Ww + t.x) * cg + (c0 >> 3);
+                    const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
+                    for (int pr = 0; pr < targets; ++pr) {
+                        uint4 *o = reinterpret_cast<uint4 *>(ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32) + off;
+                        o[0] = q0;
+                        if (c0 + 8 < ep.cout) o[1] = q1;
+                    }
                 } else if constexpr (MODE == EPI_F32_HEAD) {
                     // 1x1x1 conv on the voxel's channel vector (registers) with the head in shared memory
                     const float *hb = seed + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;

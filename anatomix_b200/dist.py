@@ -86,40 +86,105 @@ class ShardedExtractor:
         return full
 
 
-class FusedGatherExtractor:
-    """Batch-sharded extraction where the all-gather is fused into the last conv:
-    its epilogue stores every output tile into all ranks' gather buffers over NVLink
-    (peer pointers from torch symmetric memory), so no separate collective runs.
+class FeatureGather:
+    """Batch-sharded extraction with the feature all-gather done WITHOUT a library collective, over peer-mapped
+    gather buffers (torch symmetric memory -> NVLink addresses):
 
-    ``extract(batch_shard)`` takes this rank's ``[n, C_in, D, H, W]`` CUDA shard (equal
-    ``n`` on every rank) and returns the full ``[world*n, C_out, D, H, W]`` tensor,
-    which lives in symmetric memory and is overwritten by the next call."""
+    * ``mode="push"`` (default): the forward writes this rank's slice into its own gather buffer, then the copy
+      engines push that slice to every peer (`anx_push_to_peers`) on a side stream -- no SM is involved, so
+      the pushes of step k overlap the convs of step k + 1 (`submit` / `wait`);
+    * ``mode="fused"``: the last conv's epilogue stores every tile into all ranks' buffers itself
+      (`anx_engine_forward_gather`); the transfer rides inside the conv kernel.
 
-    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+    ``payload="f32"`` gathers the reference's fp32 NCDHW features (bit-identical to a local forward);
+    ``payload="cl16"`` gathers 16-bit channels-last ``[N, D, H, W, C]`` features (half the NVLink bytes; the
+    fp32 results rounded once), which `Engine.widen` turns into fp32 NCDHW locally when asked.
+
+    Every rank calls `extract` / `submit` with its own ``[n, C_in, D, H, W]`` CUDA shard (equal ``n``) the same
+    number of times.  Results live in symmetric memory and are overwritten ``depth`` submissions later."""
+
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, mode: str = "push", payload: str = "f32",
+                 depth: int = 2):
         import torch.distributed._symmetric_memory as symm_mem
+        if mode not in ("push", "fused") or payload not in ("f32", "cl16"):
+            raise ValueError("mode is 'push' or 'fused', payload 'f32' or 'cl16'")
         self._symm = symm_mem
-        self.engine = engine
+        self.engine, self.mode, self.payload, self.depth = engine, mode, payload, depth
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         if self.world > 8:
             raise ValueError("at most 8 peers (one NVSwitch box)")
-        self._buf = None
-        self._hdl = None
+        self._shape = None
+        self._bufs, self._hdls, self._done = [], [], []
+        self._comm = torch.cuda.Stream(device=engine.device)
+        self._k = 0
 
-    def _buffers(self, shape):
-        if self._buf is None or tuple(self._buf.shape) != tuple(shape):
-            self._buf = self._symm.empty(shape, dtype=torch.float32, device=self.engine.device)
-            self._hdl = self._symm.rendezvous(self._buf, self.group)
-        return self._buf, self._hdl
+    def _full_shape(self, n, d, h, w):
+        c = self.engine.output_nc
+        return (self.world * n, c, d, h, w) if self.payload == "f32" else (self.world * n, d, h, w, c)
+
+    def _ensure(self, n, d, h, w):
+        shape = self._full_shape(n, d, h, w)
+        if self._shape != shape:
+            dtype = torch.float32 if self.payload == "f32" else self.engine.storage_dtype
+            self._bufs = [self._symm.empty(shape, dtype=dtype, device=self.engine.device) for _ in range(self.depth)]
+            self._hdls = [self._symm.rendezvous(b, self.group) for b in self._bufs]
+            self._done = [None] * self.depth
+            self._shape = shape
+
+    def submit(self, shard: torch.Tensor) -> int:
+        """Queues forward + gather of one shard; returns the slot to pass to `wait`."""
+        from . import _lib
+        n, _, d, h, w = shard.shape
+        self._ensure(n, d, h, w)
+        b = self._k % self.depth
+        self._k += 1
+        buf, hdl = self._bufs[b], self._hdls[b]
+        dev = self.engine.device
+        main = torch.cuda.current_stream(dev)
+        mine = buf[self.rank * n:(self.rank + 1) * n]
+        if self.mode == "fused":
+            hdl.barrier()                               # every rank is done reading this buffer's previous content
+            self.engine.forward_gather(shard, list(hdl.buffer_ptrs), self.rank,
+                                       _lib.PAYLOAD_F32_NCDHW if self.payload == "f32" else _lib.PAYLOAD_CL16)
+            hdl.barrier()                               # every rank's stores have landed everywhere
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._done[b] = ev
+            return b
+        if self.payload == "f32":
+            self.engine.forward(shard, out=mine)
+        else:
+            self.engine.forward_cl16(shard, out=mine)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        slot_bytes = mine.numel() * mine.element_size()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            hdl.barrier()                               # peers have consumed what this buffer held before
+            self.engine.push_to_peers(mine, [p + self.rank * slot_bytes for p in hdl.buffer_ptrs], self.rank)
+            hdl.barrier()                               # all slices have landed in every rank's buffer
+            ev = torch.cuda.Event()
+            ev.record(self._comm)
+        self._done[b] = ev
+        return b
+
+    def wait(self, slot: int) -> torch.Tensor:
+        """The gathered tensor of `slot`; the current stream waits until every rank's slice is in place."""
+        torch.cuda.current_stream(self.engine.device).wait_event(self._done[slot])
+        return self._bufs[slot]
 
     def extract(self, shard: torch.Tensor) -> torch.Tensor:
-        n, _, d, h, w = shard.shape
-        buf, hdl = self._buffers((self.world * n, self.engine.output_nc, d, h, w))
-        hdl.barrier()                                   # peers are done reading the previous result
-        self.engine.forward_allgather(shard, list(hdl.buffer_ptrs), self.rank)
-        hdl.barrier()                                   # every rank's stores have landed everywhere
-        return buf
+        return self.wait(self.submit(shard))
+
+
+class FusedGatherExtractor(FeatureGather):
+    """`FeatureGather` in its fused form (kept under its round-1 name): the last conv's epilogue stores into all
+    ranks' fp32 gather buffers."""
+
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+        super().__init__(engine, group, mode="fused", payload="f32", depth=1)
 
 
 # ------------------------------------------------------------------ depth slabs

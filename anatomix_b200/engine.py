@@ -245,6 +245,95 @@ class Engine:
             self._check(self.lib.anx_engine_forward_allgather(
                 self._h, x.data_ptr(), arr, world, rank, n, d, h, w, ws.data_ptr(), ws.numel(), stream))
 
+    # -- 16-bit channels-last payload ---------------------------------------------
+    @property
+    def storage_dtype(self) -> torch.dtype:
+        """torch dtype of stored activations and of the CL16 payload (anx_engine_storage_type)."""
+        return torch.bfloat16 if self.lib.anx_engine_storage_type(self._h) == 0 else torch.float16
+
+    def forward_cl16(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward that writes the features as a 16-bit channels-last ``[N, D, H, W, C]`` tensor (the fp32
+        results rounded once; half the bytes of the drop-in output).  ``out.permute(0, 4, 1, 2, 3)`` is the
+        logical NCDHW view (torch's channels_last_3d)."""
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        if out is None:
+            out = torch.empty((n, d, h, w, self.output_nc), dtype=self.storage_dtype, device=self.device)
+        elif tuple(out.shape) != (n, d, h, w, self.output_nc) or out.dtype != self.storage_dtype \
+                or out.device != self.device or not out.is_contiguous():
+            raise ValueError(f"`out` must be a contiguous {self.storage_dtype} tensor [N, D, H, W, C] on {self.device}")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_cl16(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def widen(self, cl16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """16-bit channels-last ``[N, D, H, W, C]`` -> fp32 NCDHW (anx_widen_cl16_f32)."""
+        n, d, h, w, c = cl16.shape
+        if out is None:
+            out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=cl16.device)
+        with torch.cuda.device(cl16.device):
+            st = self.lib.anx_widen_cl16_f32(cl16.data_ptr(), out.data_ptr(), n, c, d, h, w,
+                                             0 if cl16.dtype == torch.bfloat16 else 1,
+                                             torch.cuda.current_stream(cl16.device).cuda_stream)
+        if st != _lib.ANX_OK:
+            raise EngineError(st, "anx_widen_cl16_f32")
+        return out
+
+    def forward_gather(self, x: torch.Tensor, peer_ptrs, rank: int, payload: int = _lib.PAYLOAD_F32_NCDHW):
+        """Forward whose last conv stores into every rank's gather buffer in the chosen payload
+        (anx_engine_forward_gather)."""
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        ws = self.workspace(n, d, h, w)
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_gather(
+                self._h, x.data_ptr(), arr, world, rank, payload, n, d, h, w, ws.data_ptr(), ws.numel(), stream))
+
+    def push_to_peers(self, src: torch.Tensor, peer_dst_ptrs, rank: int):
+        """Copy-engine push of ``src`` (contiguous) to ``peer_dst_ptrs[r]`` for every r != rank, on the current
+        stream (anx_push_to_peers)."""
+        world = len(peer_dst_ptrs)
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_dst_ptrs])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_push_to_peers(self._h, src.data_ptr(), arr, world, rank,
+                                                   src.numel() * src.element_size(), stream))
+
+    def forward_slab(self, x: torch.Tensor, out: torch.Tensor, ws: torch.Tensor, lower_ws: int, upper_ws: int,
+                     flags: int, lower_flags: int, upper_flags: int):
+        """Depth-slab forward with the halo exchange inside the engine (anx_engine_forward_slab).  ``ws`` is this
+        rank's peer-visible workspace; the integer arguments are device addresses (0 = no neighbour)."""
+        n, d, h, w = out.shape[0], out.shape[2], out.shape[3], out.shape[4]
+        links = _lib.SlabLinks(C.sizeof(_lib.SlabLinks), lower_ws or None, upper_ws or None, flags,
+                               lower_flags or None, upper_flags or None)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_slab(
+                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), C.byref(links), stream))
+
+    def forward_host_cl16(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
+                          dev_out: torch.Tensor):
+        """`forward_host` with the 16-bit channels-last payload: ``out_host`` / ``dev_out`` are
+        ``[N, D, H, W, C]`` tensors of `storage_dtype` (half the download of the fp32 drop-in output)."""
+        n, _, d, h, w = x_host.shape
+        shape = (n, d, h, w, self.output_nc)
+        for t, dev, what in ((out_host, "cpu", "out_host"), (dev_out, "cuda", "dev_out")):
+            if tuple(t.shape) != shape or t.dtype != self.storage_dtype or t.device.type != dev or not t.is_contiguous():
+                raise ValueError(f"`{what}` must be a contiguous {self.storage_dtype} {dev} tensor of shape {shape}")
+        self._check_out(dev_in, (n, self.input_nc, d, h, w), "dev_in")
+        ws = self.workspace(n, d, h, w)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_host_ex(
+                self._h, x_host.data_ptr(), out_host.data_ptr(), _lib.PAYLOAD_CL16, n, d, h, w, dev_in.data_ptr(),
+                dev_out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+
     def forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
                      dev_out: torch.Tensor):
         """End-to-end call on (pinned) host buffers; see anx_engine_forward_host."""

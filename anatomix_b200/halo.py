@@ -66,7 +66,12 @@ class DepthSlabExtractor:
     tensor) and gets its own slab of features, or the whole feature volume with
     ``gather=True``."""
 
-    def __init__(self, cfg: dict, state: dict, device, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, cfg: dict, state: dict, device, group: Optional[dist.ProcessGroup] = None,
+                 in_engine_exchange: Optional[bool] = None):
+        """``in_engine_exchange``: run the halo protocol inside the engine (`anx_engine_forward_slab`: peer stores
+        into the neighbours' shells + flag words, no host code between launches) instead of the step-wise
+        NCCL send/recv protocol.  Default: whenever it applies (several ranks, CUDA, symmetric memory available,
+        no InstanceNorm -- whose statistics need an all-reduce between launches --, slabs of equal depth)."""
         if cfg.get("norm", "batch") not in ("batch", "none", "instance") \
                 or cfg.get("interp", "nearest") not in ("nearest", "trilinear"):
             raise NotImplementedError("depth-slab mode covers batch / instance / no norm with nearest / trilinear upsampling")
@@ -77,6 +82,39 @@ class DepthSlabExtractor:
         self.engine = Engine(cfg, device, flags=_lib.FLAG_DEPTH_HALO_INPUT)
         self.engine.load_state(state)
         self.steps = self.engine.step_table()
+        can = self.world > 1 and cfg.get("norm", "batch") != "instance"
+        self.in_engine_exchange = can if in_engine_exchange is None else (in_engine_exchange and can)
+        self._symm_ws = {}           # (n, d, h, w) -> (workspace, handle, flags, flags handle)
+
+    def _peer_workspace(self, n, d, h, w):
+        """This rank's workspace and flag words in symmetric memory (peer-mapped), allocated once per shape."""
+        key = (n, d, h, w)
+        got = self._symm_ws.get(key)
+        if got is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            ws = symm_mem.empty(self.engine.workspace_bytes(n, d, h, w), dtype=torch.uint8, device=self.engine.device)
+            ws.zero_()
+            flags = symm_mem.empty(64, dtype=torch.int32, device=self.engine.device)
+            flags.zero_()
+            h_ws, h_fl = symm_mem.rendezvous(ws, grp), symm_mem.rendezvous(flags, grp)
+            torch.cuda.synchronize(self.engine.device)
+            h_fl.barrier()                      # every rank's flags are zero before anyone publishes
+            got = (ws, h_ws, flags, h_fl)
+            self._symm_ws = {key: got}          # one shape at a time: these buffers are large
+        return got
+
+    def forward_slab(self, x: torch.Tensor, out: torch.Tensor):
+        """One depth-slab forward through `anx_engine_forward_slab` on this rank's slab input `x` (neighbour
+        planes attached) into `out`; asynchronous on the current stream."""
+        n, d, h, w = out.shape[0], out.shape[2], out.shape[3], out.shape[4]
+        ws, h_ws, flags, h_fl = self._peer_workspace(n, d, h, w)
+        lo, hi = self.rank - 1, self.rank + 1
+        self.engine.forward_slab(
+            x, out, ws,
+            h_ws.buffer_ptrs[lo] if lo >= 0 else 0, h_ws.buffer_ptrs[hi] if hi < self.world else 0,
+            h_fl.buffer_ptrs[self.rank],
+            h_fl.buffer_ptrs[lo] if lo >= 0 else 0, h_fl.buffer_ptrs[hi] if hi < self.world else 0)
 
     def _exchange(self, ws, table, buf, goff, groups, n, d, h, w):
         off, nbytes, level, gtot = table[buf]
@@ -99,6 +137,10 @@ class DepthSlabExtractor:
         self.engine.set_slab(self.rank > 0, self.rank < self.world - 1, depth if self.world > 1 else 0)
         x = slab_input_with_halo(volume, z_lo, z_hi).to(self.engine.device, torch.float32)
         out = torch.empty((n, self.cfg["output_nc"], d, h, w), dtype=torch.float32, device=self.engine.device)
+        bounds = slab_bounds(depth, self.world, self.cfg["num_downs"])
+        if self.in_engine_exchange and len({b[1] - b[0] for b in bounds}) == 1:
+            self.forward_slab(x, out)
+            return self._gather(out, depth) if gather else out
         ws = self.engine.workspace(n, d, h, w)
         table = self.engine.buffer_table(n, d, h, w)
         def stats_view(i):
@@ -114,6 +156,9 @@ class DepthSlabExtractor:
             world=self.world)
         if not gather or self.world == 1:
             return out
+        return self._gather(out, depth)
+
+    def _gather(self, out: torch.Tensor, depth: int) -> torch.Tensor:
         # slabs have equal depth unless depth/unit is not a multiple of world: gather plane-major, then permute back
         sizes = [b[1] - b[0] for b in slab_bounds(depth, self.world, self.cfg["num_downs"])]
         if len(set(sizes)) != 1:

@@ -81,6 +81,8 @@ typedef struct anx_unet_desc {
 /* Keep the decoder's level-0 conv as one launch over the materialised upsampled tensor instead of
  * evaluating its upsampled half at low resolution (tests use this to compare code paths). */
 #define ANX_FLAG_NO_UPCONV 16u
+/* Run the thin 16 -> 16 layers on the generic tile kernel instead of the row kernel (tests compare the two). */
+#define ANX_FLAG_NO_ROWS 32u
 
 /* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
  * device constants; no parameters yet. */
@@ -162,6 +164,58 @@ anx_status anx_engine_forward_allgather(anx_engine *engine, const float *in_ncdh
                                         int32_t n, int32_t d, int32_t h, int32_t w,
                                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same fused gather with a selectable payload.  ANX_PAYLOAD_F32_NCDHW: fp32 [world*n, C, D, H, W] buffers
+ * (bit-identical to anx_engine_forward on every rank).  ANX_PAYLOAD_CL16: 16-bit channels-last
+ * [world*n, D, H, W, C] buffers in the engine's storage type (anx_engine_storage_type) -- half the NVLink
+ * bytes, 1 KB contiguous per warp store; the values are the fp32 results rounded once to 16 bits, and
+ * anx_widen_cl16_f32 turns a gathered buffer into the reference's fp32 NCDHW layout locally.  With
+ * world = 1, rank = 0 this is a plain forward that writes the chosen payload (anx_engine_forward_cl16). */
+enum { ANX_PAYLOAD_F32_NCDHW = 0, ANX_PAYLOAD_CL16 = 1 };
+anx_status anx_engine_forward_gather(anx_engine *engine, const float *in_ncdhw,
+                                     void *const *out_peers, int32_t world, int32_t rank, int32_t payload,
+                                     int32_t n, int32_t d, int32_t h, int32_t w,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+anx_status anx_engine_forward_cl16(anx_engine *engine, const float *in_ncdhw, void *out_cl16,
+                                   int32_t n, int32_t d, int32_t h, int32_t w,
+                                   void *workspace, size_t workspace_bytes, void *stream);
+/* 0 = bf16, 1 = fp16: the 16-bit type of stored activations and of the CL16 payload. */
+int32_t anx_engine_storage_type(const anx_engine *engine);
+/* 16-bit channels-last [n, D, H, W, channels] -> fp32 NCDHW [n, channels, D, H, W] on the current device. */
+anx_status anx_widen_cl16_f32(const void *src_cl16, float *dst_ncdhw, int64_t n, int32_t channels,
+                              int32_t d, int32_t h, int32_t w, int32_t storage_type, void *stream);
+
+/* Feature all-gather by the copy engines: copies `bytes` from `src` (this rank's slice, already inside its
+ * own gather buffer) to `peer_dst[r]` for every r != rank (NVLink-mapped addresses of this rank's slot in
+ * rank r's gather buffer), one copy per destination on internal streams forked from / joined back into
+ * `stream`.  No SM is used, so the pushes of step k overlap the convs of step k + 1 when `stream` is a side
+ * stream.  The ranks synchronise afterwards (a barrier) before reading.  Replaces: the `ncclAllGather` of
+ * BASELINE.json configs[3]. */
+anx_status anx_push_to_peers(anx_engine *engine, const void *src, void *const *peer_dst,
+                             int32_t world, int32_t rank, size_t bytes, void *stream);
+
+/* Depth-slab forward of ONE oversized volume split along D over the GPUs of a box (BASELINE.json
+ * configs[4]) with the halo exchange done by the engine: after every launch that produces an activation
+ * tensor, one small kernel stores this slab's two boundary planes of that tensor straight into the
+ * neighbours' shell planes (through `lower_workspace` / `upper_workspace`, the neighbours' workspaces
+ * mapped into this process, e.g. torch symmetric memory; NULL at a global face), publishes a sequence
+ * number in their flag words and waits for theirs -- no host code, library collective or staging copy
+ * between launches.  Requirements: every rank calls this the same number of times with the same shape
+ * (slabs of equal depth: the workspace layout must be identical on all ranks); `flags` points to two
+ * zero-initialised uint32 in peer-visible memory ([0] written by the lower, [1] by the upper neighbour),
+ * `lower_flags` / `upper_flags` are the neighbours' `flags` mapped here; anx_engine_set_slab has been
+ * called with the matching faces; the engine was created with ANX_FLAG_DEPTH_HALO_INPUT (the input
+ * carries the neighbours' boundary planes).  BatchNorm(eval) / no-norm networks only: InstanceNorm needs
+ * the caller's all-reduce between launches (anx_engine_run_steps + anx_engine_step_stats). */
+typedef struct anx_slab_links {
+    uint32_t struct_size;                  /* = sizeof(anx_slab_links) */
+    void *lower_workspace, *upper_workspace;
+    uint32_t *flags, *lower_flags, *upper_flags;
+} anx_slab_links;
+anx_status anx_engine_forward_slab(anx_engine *engine, const float *in_ncdhw, float *out_ncdhw,
+                                   int32_t n, int32_t d, int32_t h, int32_t w,
+                                   void *workspace, size_t workspace_bytes,
+                                   const anx_slab_links *links, void *stream);
+
 /* Same call for HOST buffers (pinned memory recommended): copies the input to
  * `dev_in`, runs the forward, copies `dev_out` back, all queued on `stream`.
  * `dev_in` / `dev_out` are caller-owned device staging buffers of the input /
@@ -170,6 +224,14 @@ anx_status anx_engine_forward_host(anx_engine *engine, const float *in_host, flo
                                    int32_t n, int32_t d, int32_t h, int32_t w,
                                    float *dev_in, float *dev_out,
                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Host-buffer forward with a selectable output payload: ANX_PAYLOAD_CL16 downloads the features as 16-bit
+ * channels-last [N, D, H, W, C] (half the PCIe bytes of the fp32 drop-in output; `out_host` / `dev_out` are
+ * then buffers of that size and type). */
+anx_status anx_engine_forward_host_ex(anx_engine *engine, const float *in_host, void *out_host,
+                                      int32_t payload, int32_t n, int32_t d, int32_t h, int32_t w,
+                                      float *dev_in, void *dev_out,
+                                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- rows next to the hot path -------------------------------------------
  *

@@ -85,6 +85,23 @@ def mint_g7(Unet, sd):
     np.savez_compressed(os.path.join(HERE, "g7_6m_taps.npz"), **g)
 
 
+def mint_g8(Unet):
+    """G8: the 94M `anatomix-dev` config at the BASELINE volume size (1 x 128^3), seeded default init (seed 0, as G4);
+    G9: the same network at 64^3 with every conv weight scaled x30 -- the raw pre-norm conv outputs, which the engine
+    stores in fp16 before normalising them, are 30x larger there (InstanceNorm undoes the scale up to its eps)."""
+    torch.manual_seed(0)
+    m94 = Unet(**CFG_94M).eval()
+    with torch.no_grad():
+        y = m94(rand_input((1, 1, 128, 128, 128), 0))
+        np.savez_compressed(os.path.join(HERE, "g8_94m_128.npz"), out_s8=sub(y, 8), mom=moments(y),
+                            probe=y[0, :4, 64, 64, 64].numpy())
+        for k, v in m94.state_dict().items():
+            if k.endswith(".weight"):
+                v.mul_(30.0)
+        y = m94(rand_input((1, 1, 64, 64, 64), 0))
+        np.savez_compressed(os.path.join(HERE, "g9_94m_64_w30.npz"), out_s4=sub(y, 4), mom=moments(y))
+
+
 def main():
     sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.abspath(os.path.join(HERE, "..", ".."))]
     sys.path.insert(0, REF)
@@ -92,6 +109,10 @@ def main():
     import anatomix.model.network as net
     assert net.__file__.startswith(REF), net.__file__
     torch.set_num_threads(os.cpu_count())
+    if sys.argv[1:] == ["g8"]:             # add G8 / G9 without re-minting the others
+        mint_g8(Unet)
+        write_manifest()
+        return
     if sys.argv[1:] == ["g7"]:             # add G7 without re-minting the others
         mint_g7(Unet, torch.load(os.path.join(REF, "model-weights", "anatomix.pth"), map_location="cpu"))
         write_manifest()
@@ -154,6 +175,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "g4_94m_64.npz"), **g)
 
     mint_g7(Unet, sd)
+    mint_g8(Unet)
     write_manifest()
 
 

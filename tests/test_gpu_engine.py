@@ -514,15 +514,14 @@ def test_native_blend_kernel_matches_torch_accumulate():
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256), (3, 1, 16, 8, 128), (1, 1, 48, 40, 128)])
-def test_row_kernel_matches_generic_kernel(shape, monkeypatch):
+def test_row_kernel_matches_generic_kernel(shape):
     """conv3_rows_kernel (dy and dz folded into N, lanes = one 128-voxel row) against the generic tile kernel
     on the same packed 16-bit operands: only the fp32 summation order differs."""
     cfg = small_cfg()
     state = O.random_state(cfg, seed=13)
     x = rand_input(shape, 19)
-    monkeypatch.setenv("ANX_ROWS", "0")
-    ref = make_engine(cfg, state).forward(x.cuda())
-    monkeypatch.setenv("ANX_ROWS", "1")
+    from anatomix_b200 import _lib
+    ref = make_engine(cfg, state, flags=_lib.FLAG_NO_ROWS).forward(x.cuda())
     eng = make_engine(cfg, state)
     got = eng.forward(x.cuda())
     torch.cuda.synchronize()
@@ -553,3 +552,131 @@ def test_row_kernel_variants(cfgkw, flags):
     assert torch.isfinite(got).all()
     r, c = rel_l2(got.cpu(), want), min_cosine(got.cpu(), want)
     assert r <= LOOSE_REL and c >= LOOSE_COS, f"rel-L2 {r:.3e}, min cosine {c:.5f}"
+
+
+def _seeded_94m():
+    from conftest import CFG_94M
+    from anatomix_b200 import Unet
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_94M)
+    return CFG_94M, m.state_dict()
+
+
+def test_g8_94m_at_the_baseline_volume_size():
+    """BASELINE configs[2] network at its volume size (1 x 128^3) against golden G8 minted from the unmodified
+    reference (seeded default init: the released 94M weights are Hub-only)."""
+    cfg, sd = _seeded_94m()
+    g = golden("g8_94m_128.npz")
+    x = rand_input((1, 1, 128, 128, 128), 0)
+    y = make_engine(cfg, sd).forward(x.cuda()).cpu()
+    assert torch.isfinite(y).all()
+    got, want = y[:, :, ::8, ::8, ::8], torch.from_numpy(g["out_s8"])
+    r, c = rel_l2(got, want), min_cosine(got, want)
+    print(f"G8 94M 1x128^3: rel-L2 {r:.3e}, min cosine {c:.5f}")
+    assert r <= LOOSE_REL and c >= LOOSE_COS, f"G8: rel-L2 {r:.3e}, min cosine {c:.5f}"
+    assert abs(y.double().mean().item() - g["mom"][0]) < 2e-2 and abs(y.double().std().item() - g["mom"][1]) < 2e-2
+    # the batch of BASELINE configs[2] (4 volumes): per-sample independence, determinism
+    xb = torch.cat([x, rand_input((1, 1, 128, 128, 128), 1), x, x]).cuda()
+    eng = make_engine(cfg, sd)
+    yb = eng.forward(xb)
+    torch.cuda.synchronize()
+    assert torch.equal(yb[0], yb[2]) and torch.equal(yb[0], yb[3]) and torch.equal(yb[0].cpu(), y[0])
+
+
+def test_g9_raw_prenorm_store_survives_large_conv_outputs():
+    """The InstanceNorm path stores the RAW conv output in fp16 and normalises it in place afterwards.  With every
+    conv weight scaled x30 the raw tensors are 30x larger (the normalisation undoes the scale): neither overflow
+    nor lost resolution may show -- golden G9 from the reference with the same scaled weights."""
+    cfg, sd = _seeded_94m()
+    sd = {k: (v * 30.0 if k.endswith(".weight") else v) for k, v in sd.items()}
+    g = golden("g9_94m_64_w30.npz")
+    x = rand_input((1, 1, 64, 64, 64), 0)
+    y = make_engine(cfg, sd).forward(x.cuda()).cpu()
+    assert torch.isfinite(y).all()
+    got, want = y[:, :, ::4, ::4, ::4], torch.from_numpy(g["out_s4"])
+    r, c = rel_l2(got, want), min_cosine(got, want)
+    print(f"G9 94M x30 weights: rel-L2 {r:.3e}, min cosine {c:.5f}")
+    assert r <= LOOSE_REL and c >= LOOSE_COS, f"G9: rel-L2 {r:.3e}, min cosine {c:.5f}"
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 32, 32, 32), (1, 1, 32, 32, 128)])    # generic tile kernel / row kernel
+def test_channels_last_16bit_output_and_widen(state_6m, shape):
+    """ANX_PAYLOAD_CL16: the features as 16-bit channels-last [N, D, H, W, C] are the fp32 output rounded once."""
+    x = rand_input(shape, 12)
+    eng = make_engine(CFG_6M, state_6m)
+    y = eng.forward(x.cuda())
+    y16 = eng.forward_cl16(x.cuda())
+    torch.cuda.synchronize()
+    assert y16.dtype == torch.bfloat16 and tuple(y16.shape) == (shape[0],) + shape[2:] + (16,)
+    assert torch.equal(y16.permute(0, 4, 1, 2, 3), y.to(torch.bfloat16))
+    wide = eng.widen(y16)
+    torch.cuda.synchronize()
+    assert torch.equal(wide, y.to(torch.bfloat16).float())
+    # host-buffer entry point with the 16-bit payload
+    n, _, d, h, w = shape
+    xh, oh = x.pin_memory(), torch.empty((n, d, h, w, 16), dtype=torch.bfloat16).pin_memory()
+    dev_in, dev_out = torch.empty(shape, device="cuda"), torch.empty((n, d, h, w, 16), dtype=torch.bfloat16, device="cuda")
+    eng.forward_host_cl16(xh, oh, dev_in, dev_out)
+    torch.cuda.synchronize()
+    assert torch.equal(oh, y16.cpu())
+
+
+def test_channels_last_output_of_a_32_channel_instance_norm_network():
+    cfg = small_cfg(norm="instance", num_downs=1, ngf=32, output_nc=32, norm_eps=1e-2)
+    state = O.random_state(cfg, seed=41)
+    x = rand_input((1, 1, 8, 16, 24), 42)
+    eng = make_engine(cfg, state)
+    y, y16 = eng.forward(x.cuda()), eng.forward_cl16(x.cuda())
+    torch.cuda.synchronize()
+    assert y16.dtype == torch.float16 and torch.equal(y16.permute(0, 4, 1, 2, 3), y.to(torch.float16))
+
+
+def test_forward_argument_validation(state_6m):
+    eng = make_engine(CFG_6M, state_6m)
+    x = rand_input((1, 1, 32, 32, 32), 0).cuda()
+    with pytest.raises(ValueError):
+        eng.forward(x, out=torch.empty((1, 16, 32, 32, 16), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.forward(x, out=torch.empty((1, 16, 32, 32, 32), device="cuda", dtype=torch.float16))
+    with pytest.raises(ValueError):
+        eng.forward(x, out=torch.empty((1, 16, 32, 32, 64), device="cuda")[..., ::2])
+
+
+def test_data_edits_reach_the_engine(state_6m, monkeypatch):
+    """In-place edits through `.data` bump no version counter (reference pretraining_networks.py:695-713 initialises
+    weights that way): `invalidate_engine()` re-packs at once, the periodic content check catches it otherwise."""
+    from anatomix_b200 import Unet
+    from anatomix_b200 import engine as E
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    x = rand_input((1, 1, 32, 32, 32), 2).cuda()
+    with torch.no_grad():
+        y = m(x)
+        m.model[65].weight.data.mul_(2.0)
+        m.invalidate_engine()
+        y2 = m(x)
+        assert rel_l2(y2.cpu(), 2 * y.cpu()) < 1e-2
+        monkeypatch.setattr(E, "VERIFY_EVERY", 1)
+        m.model[65].weight.data.mul_(0.5)
+        y3 = m(x)
+        assert rel_l2(y3.cpu(), y.cpu()) < 1e-2
+
+
+def test_hooks_send_the_call_down_the_stock_loop(state_6m):
+    from anatomix_b200 import Unet
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    seen = []
+    h = m.model[3].register_forward_hook(lambda mod, i, o: seen.append(tuple(o.shape)))
+    x = rand_input((1, 1, 32, 32, 32), 2).cuda()
+    with torch.no_grad():
+        assert "hooks" in m.engine_ineligible_reason(x)
+        m(x)
+        assert seen == [(1, 16, 32, 32, 32)]
+        h.remove()
+        assert m.engine_ineligible_reason(x) is None

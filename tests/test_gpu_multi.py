@@ -54,17 +54,54 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         assert torch.equal(got2, eng.forward(batch.to(dev) * 0.5))
 
-        # (2) one volume, depth split in two slabs of 32 planes with per-layer halo planes
-        vol = torch.rand(1, 1, 64, 32, 48, generator=torch.Generator().manual_seed(4))
-        slab = DepthSlabExtractor(CFG_6M, state, dev)
-        got = slab.extract(vol, gather=True)
-        want = eng.forward(vol.to(dev))
+        # (1c) copy-engine push gather (anx_push_to_peers), fp32 payload: bit-identical as well, buffers reused
+        from anatomix_b200.dist import FeatureGather
+        push = FeatureGather(eng, mode="push", payload="f32")
+        for scale in (1.0, 0.5, 0.25):                      # three submissions: both buffers of the ring are reused
+            got = push.extract(batch[lo:hi].to(dev) * scale)
+            torch.cuda.synchronize()
+            assert torch.equal(got, eng.forward(batch.to(dev) * scale)), "push gather differs from the single-GPU result"
+        # pipelined use: two submissions in flight before the first is read
+        s0 = push.submit(batch[lo:hi].to(dev))
+        s1 = push.submit(batch[lo:hi].to(dev) * 2.0)
+        g0 = push.wait(s0).clone()
+        g1 = push.wait(s1).clone()
         torch.cuda.synchronize()
-        err = (got - want).abs().max().item()
-        rel = ((got - want).norm() / want.norm()).item()
-        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
-            f.write(f"{err} {rel}\n")
-        assert rel < 1e-3, f"depth-slab result differs from single-GPU: max abs {err}, rel-L2 {rel}"
+        assert torch.equal(g0, ref) and torch.equal(g1, eng.forward(batch.to(dev) * 2.0))
+
+        # (1d) 16-bit channels-last payload, pushed and fused: equal to the local 16-bit forward of the whole batch,
+        # and, widened, within one 16-bit rounding of the fp32 features
+        local16 = eng.forward_cl16(batch.to(dev))
+        for mode in ("push", "fused"):
+            g16 = FeatureGather(eng, mode=mode, payload="cl16").extract(batch[lo:hi].to(dev))
+            torch.cuda.synchronize()
+            assert g16.dtype == eng.storage_dtype and tuple(g16.shape) == (4, 32, 32, 32, 16)
+            assert torch.equal(g16, local16), f"{mode} cl16 gather differs from the local 16-bit forward"
+            wide = eng.widen(g16)
+            torch.cuda.synchronize()
+            assert torch.equal(wide, ref.to(eng.storage_dtype).float()), "widened payload is not the rounded fp32 output"
+
+        # (2) one volume, depth split in two slabs of 32 planes with per-layer halo planes: the in-engine
+        # exchange (peer stores + flags, anx_engine_forward_slab) and the step-wise NCCL protocol
+        vol = torch.rand(1, 1, 64, 32, 48, generator=torch.Generator().manual_seed(4))
+        want = eng.forward(vol.to(dev))
+        for in_engine in (True, False):
+            slab = DepthSlabExtractor(CFG_6M, state, dev, in_engine_exchange=in_engine)
+            assert slab.in_engine_exchange == in_engine
+            for rep in range(2):                             # twice: sequence numbers carry over between forwards
+                got = slab.extract(vol, gather=True)
+                torch.cuda.synchronize()
+                err = (got - want).abs().max().item()
+                rel = ((got - want).norm() / want.norm()).item()
+                with open(os.path.join(out_dir, f"rank{rank}.txt"), "a") as f:
+                    f.write(f"slab in_engine={in_engine} rep={rep}: max abs {err} rel-L2 {rel}\n")
+                assert err == 0.0, f"depth-slab result (in_engine={in_engine}) differs from single-GPU: max abs {err}, rel-L2 {rel}"
+        # a 128-wide volume: the row kernel's launches take part in the exchange as well
+        vol = torch.rand(1, 1, 64, 32, 128, generator=torch.Generator().manual_seed(6))
+        want = eng.forward(vol.to(dev))
+        got = DepthSlabExtractor(CFG_6M, state, dev).extract(vol, gather=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), "depth-slab result differs on the row-kernel shape"
 
         # (3) the same partition for an InstanceNorm / AvgPool / trilinear network (`anatomix-dev` style):
         # whole-volume statistics via an all-reduce of the per-conv sums, neighbour planes in the upsample

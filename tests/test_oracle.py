@@ -67,6 +67,19 @@ def test_g4_94m_instance_avg_trilinear():
         np.testing.assert_allclose(got, g[f"tap{i}"], atol=5e-4, rtol=1e-3, err_msg=f"tap {i}")
 
 
+def test_g9_94m_with_conv_weights_scaled_by_30():
+    """Golden G9 (the reference with every conv weight x30: InstanceNorm undoes the scale up to its eps)."""
+    import contextlib, io
+    from anatomix_b200 import Unet
+    g = golden("g9_94m_64_w30.npz")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sd = Unet(**CFG_94M).state_dict()
+    sd = {k: (v * 30.0 if k.endswith(".weight") else v) for k, v in sd.items()}
+    y = O.unet_forward(CFG_94M, sd, rand_input((1, 1, 64, 64, 64), 0))
+    np.testing.assert_allclose(y[:, :, ::4, ::4, ::4].numpy(), g["out_s4"], atol=5e-4, rtol=1e-3)
+
+
 def test_g5_train_mode_batch_stats(state_6m):
     g = golden("g5_6m_train.npz")
     y = O.unet_forward(CFG_6M, state_6m, rand_input((1, 1, 32, 32, 32), 0), training=True)

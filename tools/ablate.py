@@ -1,5 +1,7 @@
 """Timing experiments on the conv kernel (results are WRONG under ablation; this
-only locates the bottleneck).  Usage on a GPU box: python tools/ablate.py"""
+only locates the bottleneck).  The switches exist only in experiment builds of the library:
+    ANX_LIB_VARIANT=exp python -m anatomix_b200.build          (here, before shipping the tree to the GPU box)
+    ANX_LIB_VARIANT=exp python tools/ablate.py                 (on the GPU box)"""
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r'''
@@ -16,6 +18,8 @@ for r in range(3):
     for n, t in eng.profile(x): acc[n] = acc.get(n, 0) + t / 3
 print(" ".join(f"{n.split('_')[0]}:{acc[n]*1000:.0f}" for n in acc if n.startswith("conv")))
 ''' % (ROOT, ROOT)
+if not os.environ.get("ANX_LIB_VARIANT"):
+    sys.exit("set ANX_LIB_VARIANT=<tag> (an -DANX_EXPERIMENTS build): the product library ignores ANX_ABLATE")
 for ab in sys.argv[1:] or ["0", "1", "2", "4", "8", "3", "5", "6", "15"]:
     env = dict(os.environ, ANX_ABLATE=ab)
     r = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
