@@ -311,7 +311,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                             pd[gstride] = q1;
                             const int rep = ep.dst.shell_rep;
                             const int mdx = mirror_delta(x, Ww, rep), mdy = mirror_delta(y, Hh, rep),
-                                      mdz = mirror_delta(z, Dd, rep);
+                                      mdz = mirror_delta_z(z, Dd, rep, ep.dst.z_open);
                             if (mdx | mdy | mdz) {
                                 store_mirrors(pd, q0, mdz, mdy, mdx, rowp, plane);
                                 store_mirrors(pd + gstride, q1, mdz, mdy, mdx, rowp, plane);

@@ -492,6 +492,7 @@ ActView view_of(const anx_engine *e, const ShapePlan &p, int buf, int group_offs
     v.H = p.H >> b.level;
     v.W = p.W >> b.level;
     v.shell_rep = b.shell_rep;
+    v.z_open = (e->slab_lower ? 1 : 0) | (e->slab_upper ? 2 : 0);
     const RowLayout rl = layout_of(v.W, e->x_lead);
     v.lead = rl.lead;
     v.pitch = rl.pitch;

@@ -114,6 +114,11 @@ __device__ __forceinline__ int mirror_delta(int v, int S, int rep = 0) {
     if (rep) return v == 0 ? -1 : (v == S - 1 ? 1 : 0);      // replicate: shell cell next to the border voxel
     return v == 1 ? -2 : (v == S - 2 ? 2 : 0);
 }
+// z axis: no mirror copy into a shell plane that a neighbouring depth slab owns (ActView::z_open)
+__device__ __forceinline__ int mirror_delta_z(int v, int S, int rep, int open) {
+    const int d = mirror_delta(v, S, rep);
+    return (d < 0 && (open & 1)) || (d > 0 && (open & 2)) ? 0 : d;
+}
 
 // Stores `ngroups` (1 or 2) packed 8-channel groups of voxel (n,z,y,x) starting at
 // group g0 into a padded planar buffer, including its reflect-shell copies.
@@ -122,7 +127,7 @@ __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, i
     const size_t row = (size_t)dst.pitch, plane = row * (dst.H + 2), gstride = plane * (dst.D + 2);
     uint4 *p = dst.at(n, g0, z + 1, y + 1, x + 1);
     if (dst.D >= 4 && dst.H >= 4 && dst.W >= 4) {
-        const int dz = mirror_delta(z, dst.D, dst.shell_rep), dy = mirror_delta(y, dst.H, dst.shell_rep),
+        const int dz = mirror_delta_z(z, dst.D, dst.shell_rep, dst.z_open), dy = mirror_delta(y, dst.H, dst.shell_rep),
                   dx = mirror_delta(x, dst.W, dst.shell_rep);
         *p = q0;
         if (ngroups > 1) p[gstride] = q1;
@@ -135,7 +140,7 @@ __device__ __forceinline__ void store_padded_groups(const ActView &dst, int n, i
     // tiny tensors (a size-2 or size-3 axis mirrors one voxel to both sides): generic loops
     for (int a = 0; a < 3; ++a) {
         const int zt = mirror_target(z, dst.D, a, dst.shell_rep);
-        if (zt < 0) continue;
+        if (zt < 0 || (a == 1 && (dst.z_open & 1)) || (a == 2 && (dst.z_open & 2))) continue;
         for (int b = 0; b < 3; ++b) {
             const int yt = mirror_target(y, dst.H, b, dst.shell_rep);
             if (yt < 0) continue;

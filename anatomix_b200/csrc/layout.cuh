@@ -55,6 +55,9 @@ struct ActView {            // one tensor inside a padded planar buffer
     int group_offset;       // first group of this tensor
     int D, H, W;            // interior size
     int shell_rep;          // shell semantics written by the producer: 0 reflect (x[1] / x[S-2]), 1 replicate (x[0] / x[S-1])
+    int z_open;             // depth-slab mode: bit 0 / bit 1 = the lower / upper z face borders a neighbouring slab.  That
+                            // shell plane belongs to the NEIGHBOUR (its boundary plane is delivered into it, possibly
+                            // before this slab's own producer has run), so the producer writes no mirror copy there.
     int lead, pitch;        // row geometry: voxels in front of the x shell, voxels per row (layout_of)
     __host__ __device__ __forceinline__ size_t voxel_index(int n, int g, int zp, int yp, int xp) const {
         return ((((size_t)n * groups_total + (group_offset + g)) * (D + 2) + zp) * (H + 2) + yp) * (size_t)pitch +

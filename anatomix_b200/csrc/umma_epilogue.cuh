@@ -133,7 +133,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                         p[0] = a0;
                         p[plane] = c0q;
                         if (ngroups > 1) { p[gstride] = a1; p[gstride + plane] = c1q; }
-                        const int mz0 = mirror_delta(z, Dd, rep), mz1 = mirror_delta(z + 1, Dd, rep);
+                        const int mz0 = mirror_delta_z(z, Dd, rep, ep.dst.z_open), mz1 = mirror_delta_z(z + 1, Dd, rep, ep.dst.z_open);
                         if (mdx | mdy | mz0) {
                             store_mirrors(p, a0, mz0, mdy, mdx, rowp, plane);
                             if (ngroups > 1) store_mirrors(p + gstride, a1, mz0, mdy, mdx, rowp, plane);
@@ -247,7 +247,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                         uint4 *p = pbase + (size_t)b * plane + (size_t)(2 * cb) * gstride;
                         *p = q0;
                         if (ngroups > 1) p[gstride] = q1;
-                        const int mdz = mirror_delta(z, Dd, rep);
+                        const int mdz = mirror_delta_z(z, Dd, rep, ep.dst.z_open);
                         if (mdx | mdy | mdz) {   // shell copies: a few predicated stores, no loops
                             store_mirrors(p, q0, mdz, mdy, mdx, rowp, plane);
                             if (ngroups > 1) store_mirrors(p + gstride, q1, mdz, mdy, mdx, rowp, plane);

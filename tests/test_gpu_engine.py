@@ -680,3 +680,42 @@ def test_hooks_send_the_call_down_the_stock_loop(state_6m):
         assert seen == [(1, 16, 32, 32, 32)]
         h.remove()
         assert m.engine_ineligible_reason(x) is None
+
+
+@pytest.mark.parametrize("cfgkw,shape", [({}, (1, 1, 32, 32, 128)),                       # 6M: row kernel, fused pooling, upconv
+                                         (dict(num_downs=2, pooling="Avg", interp="trilinear"), (2, 1, 16, 16, 24))])
+def test_open_slab_faces_are_left_to_the_neighbour(state_6m, cfgkw, shape):
+    """Depth-slab mode: a shell plane at a face that borders another slab belongs to the NEIGHBOUR, whose boundary
+    plane may arrive before this slab's producer of that tensor has even started (anx_engine_forward_slab), so no
+    kernel of this slab may write there.  Sentinel-fill the workspace, run a forward with both faces open, and
+    check that every such plane is untouched; with the faces closed the same planes hold the reflect copies."""
+    from anatomix_b200 import _lib
+    from anatomix_b200.engine import Engine
+    if cfgkw:
+        cfg = small_cfg(**cfgkw)
+        state = O.random_state(cfg, seed=3)
+    else:
+        cfg, state = CFG_6M, state_6m
+    n, _, d, h, w = shape
+    eng = Engine(cfg, "cuda:0", flags=_lib.FLAG_DEPTH_HALO_INPUT)
+    eng.load_state(state)
+    x = torch.rand(n, 1, d + 2, h, w, device="cuda")
+    out = torch.empty((n, cfg["output_nc"], d, h, w), device="cuda")
+    ws = eng.workspace(n, d, h, w)
+    steps = len(eng.step_table())
+    for open_faces in (True, False):
+        eng.set_slab(open_faces, open_faces, 3 * d if open_faces else 0)
+        ws.fill_(0x7B)
+        eng.run_steps(x, out, 0, steps)
+        torch.cuda.synchronize()
+        touched = 0
+        for off, nbytes, level, groups in eng.buffer_table(n, d, h, w):
+            dl, hl, wl = d >> level, h >> level, w >> level
+            plane = (hl + 2) * eng.row_layout(wl)[1] * 16
+            v = ws[off:off + n * groups * (dl + 2) * plane].view(n, groups, dl + 2, plane)
+            touched += int((v[:, :, 0] != 0x7B).sum().item()) + int((v[:, :, dl + 1] != 0x7B).sum().item())
+        if open_faces:
+            assert touched == 0, f"{touched} bytes of neighbour-owned shell planes were written"
+        else:
+            assert touched > 0
+    eng.set_slab(False, False, 0)
