@@ -41,6 +41,7 @@ EXPORTS = [
     "anx_engine_num_taps", "anx_engine_tap_info", "anx_engine_export_tap", "anx_avgpool3d_scale_f32", "anx_blend_window_f32", "anx_engine_set_slab", "anx_engine_step_stats",
     "anx_engine_forward_gather", "anx_engine_forward_cl16", "anx_engine_storage_type", "anx_widen_cl16_f32",
     "anx_push_to_peers", "anx_engine_forward_slab", "anx_engine_forward_host_ex",
+    "anx_engine_forward_concat", "anx_channel_normalize_f32",
 ]
 
 
@@ -126,6 +127,10 @@ def load():
     lib.anx_engine_forward_slab.restype = i32
     lib.anx_engine_forward_host_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.anx_engine_forward_host_ex.restype = i32
+    lib.anx_engine_forward_concat.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.anx_engine_forward_concat.restype = i32
+    lib.anx_channel_normalize_f32.argtypes = [vp, vp, C.c_int64, i32, i32, i32, i32, i32, C.c_float, vp]
+    lib.anx_channel_normalize_f32.restype = i32
     lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_row_layout.restype = i32
     lib.anx_engine_set_head.argtypes = [vp, i32, vp, vp, i32]

@@ -320,7 +320,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                             if (ANX_ABL(g, 2)) continue;
                             // fp32 NCDHW: a warp writes one 128-byte run per channel; with a fused feature
                             // all-gather the same runs go to every rank's gather buffer over NVLink
-                            const size_t off = (size_t)(ep.sample_offset + n) * ep.cout * vol + ((size_t)z * Hh + y) * Ww + x;
+                            const size_t off = (size_t)(ep.sample_offset + n) * ep.out_nstride + ((size_t)z * Hh + y) * Ww + x;
                             const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
                             for (int pr = 0; pr < targets; ++pr) {
                                 float *po = (ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32) + off;
@@ -342,7 +342,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                         } else {
                             if (ANX_ABL(g, 2)) continue;
                             const float *hb = sh->shift + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
-                            float *po = ep.out_f32 + (size_t)n * ep.head_nc * vol + ((size_t)z * Hh + y) * Ww + x;
+                            float *po = ep.out_f32 + (size_t)n * ep.out_nstride + ((size_t)z * Hh + y) * Ww + x;
 #pragma unroll 2
                             for (int k = 0; k < ep.head_nc; ++k) {
                                 float a = hb[k];

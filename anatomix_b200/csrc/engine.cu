@@ -146,6 +146,7 @@ struct GatherArgs {           // where and how the final conv stores (one forwar
     float *peers[8] = {nullptr};     // fused feature all-gather: every rank's gather buffer (n_peers = 0: `out` only)
     int n_peers = 0, sample_offset = 0;
     int payload = ANX_PAYLOAD_F32_NCDHW;
+    size_t out_nstride = 0;          // fp32 output: floats between samples (0 = dense)
 };
 
 struct ShapePlan {            // everything that depends on (N, D, H, W, workspace)
@@ -583,6 +584,10 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         ep.n_peers = ga->n_peers;
         ep.sample_offset = ga->sample_offset;
         ep.cl16 = ga->payload == ANX_PAYLOAD_CL16 ? 1 : 0;
+    }
+    if (c.is_final) {
+        const size_t chans = e->head_nc > 0 ? (size_t)e->head_nc : (size_t)c.cout;
+        ep.out_nstride = (ga && ga->out_nstride) ? ga->out_nstride : chans * (size_t)p.D * p.H * p.W;
     }
     ep.cout = c.cout;
     ep.bias = c.d_bias;
@@ -1242,6 +1247,46 @@ anx_status anx_engine_forward_cl16(anx_engine *e, const float *in, void *out_cl1
 }
 
 int32_t anx_engine_storage_type(const anx_engine *e) { return e ? e->dt : -1; }
+
+anx_status anx_engine_forward_concat(anx_engine *e, const float *in, float *dst, int32_t dst_channels,
+                                     int32_t channel_offset, int32_t n, int32_t d, int32_t h, int32_t w,
+                                     void *workspace, size_t ws_bytes, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    const int32_t mine = anx_engine_out_channels(e);
+    if (!dst || channel_offset < 0 || dst_channels < channel_offset + mine)
+        return e->fail(ANX_ERR_BAD_ARG, "channels [%d, %d) do not fit a tensor of %d channels", channel_offset,
+                       channel_offset + mine, dst_channels);
+    const size_t vol = (size_t)d * h * w;
+    float *out = dst + (size_t)channel_offset * vol;
+    anx_status st = check_forward_args(e, in, out, n, d, h, w, workspace, ws_bytes);
+    if (st != ANX_OK) return st;
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    GatherArgs ga;
+    ga.out_nstride = (size_t)dst_channels * vol;
+    if (p->stats_bytes)
+        ANX_CUDA(e, cudaMemsetAsync(static_cast<char *>(workspace) + p->stats_offset, 0, p->stats_bytes,
+                                    static_cast<cudaStream_t>(stream)));
+    for (auto &s : e->steps) {
+        st = launch_step(e, *p, s, in, out, static_cast<cudaStream_t>(stream), &ga);
+        if (st != ANX_OK) return st;
+    }
+    return ANX_OK;
+}
+
+anx_status anx_channel_normalize_f32(const float *in, float *out, int64_t n, int32_t channels, int32_t d, int32_t h,
+                                     int32_t w, int32_t mode, float eps, void *stream) {
+    if (!in || !out || n < 1 || channels < 1 || d < 1 || h < 1 || w < 1 || (mode != 0 && mode != 1)) return ANX_ERR_BAD_ARG;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ANX_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t vol = (size_t)d * h * w;
+    channel_normalize_kernel<<<grid_for((size_t)n * vol, 256, sms, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, (size_t)n, vol, channels, mode, eps);
+    return cudaGetLastError() == cudaSuccess ? ANX_OK : ANX_ERR_CUDA;
+}
 
 anx_status anx_widen_cl16_f32(const void *src_cl16, float *dst_ncdhw, int64_t n, int32_t channels, int32_t d,
                               int32_t h, int32_t w, int32_t storage_type, void *stream) {

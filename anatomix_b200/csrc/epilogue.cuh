@@ -185,7 +185,7 @@ __device__ __forceinline__ void epilogue_store16(const Epilogue &ep, int n, int 
         for (int pr = 0; pr < targets; ++pr) {
             float *base = ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32;
             const int ns = ep.n_peers > 0 ? ep.sample_offset + n : n;
-            float *o = base + ((size_t)ns * ep.cout + c0) * plane + ((size_t)z * ep.dst.H + y) * ep.dst.W + x;
+            float *o = base + (size_t)ns * ep.out_nstride + (size_t)c0 * plane + ((size_t)z * ep.dst.H + y) * ep.dst.W + x;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (c0 + i < ep.cout) o[(size_t)i * plane] = v[i];

@@ -95,6 +95,9 @@ struct Epilogue {
     // OUT_NCDHW_F32 only: 1 = store the network output as 16-bit channels-last [N, D, H, W, cout] (type `dt`) instead
     // of fp32 NCDHW -- the compact payload of the feature all-gather and of the host download.
     int cl16;
+    // fp32 NCDHW output: floats between consecutive samples (>= channels written * D*H*W).  Larger than that when the
+    // output is a channel slice of a wider tensor (zero-copy concat with other features, anx_engine_forward_concat).
+    size_t out_nstride;
     // Fused 2x2x2 pooling (tensor-core kernel only): besides the full-resolution store, the epilogue
     // reduces each 2x2x2 block (z pair in registers, y / x pairs by warp shuffles) and writes the
     // pooled tensor with its shell.  pool_kind: -1 off, 0 max, 1 mean.

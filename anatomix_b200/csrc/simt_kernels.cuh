@@ -339,6 +339,40 @@ avgpool3d_scale_k2_kernel(const float *__restrict__ in, float *__restrict__ out,
     }
 }
 
+// ------------------------------------------------- voxelwise channel normalisation
+// Per voxel, across the C channels of fp32 [N, C, D, H, W] features (reference README.md:13,49: "voxelwise normalize the
+// features across channels to have unit norm or zero mean with unit standard deviation" before registration /
+// visualisation with the dev models):
+//   mode 0: y = x / max(||x||_2, eps)                       (torch.nn.functional.normalize(x, dim=1))
+//   mode 1: y = (x - mean_c) / (std_c + eps), unbiased std  ((x - x.mean(1, True)) / x.std(1, keepdim=True))
+// One thread per voxel, lanes along x: every channel row is read and written in 128-byte runs; two passes over the
+// channels (statistics, then scale) -- the second pass hits L1 / L2.  In place (out == in) is allowed.
+__global__ void __launch_bounds__(256)
+channel_normalize_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n_samples, size_t vol, int C,
+                         int mode, float eps) {
+    const size_t total = n_samples * vol;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = id / vol, v = id - n * vol;
+        const float *src = in + n * (size_t)C * vol + v;
+        float *dst = out + n * (size_t)C * vol + v;
+        float s = 0.0f, q = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const float x = src[(size_t)c * vol];
+            s += x;
+            q = fmaf(x, x, q);
+        }
+        float shift = 0.0f, scale;
+        if (mode == 0) {
+            scale = 1.0f / fmaxf(sqrtf(q), eps);
+        } else {
+            shift = s / (float)C;
+            const float var = fmaxf(q - s * shift, 0.0f) / (float)(C > 1 ? C - 1 : 1);
+            scale = 1.0f / (sqrtf(var) + eps);
+        }
+        for (int c = 0; c < C; ++c) dst[(size_t)c * vol] = (src[(size_t)c * vol] - shift) * scale;
+    }
+}
+
 // ------------------------------------------------------- sliding-window blend
 // One window of a sliding-window scan (MONAI-style inferer, reference convex_adam_utils.py:202-219):
 //   out[c, z0+z, y0+y, x0+x] += pred[c, z, y, x] * weight[z, y, x]      norm[z0+z, y0+y, x0+x] += weight[z, y, x]

@@ -88,7 +88,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
     if constexpr (PADDED)
         pbase = ep.dst.at(t.n, t.chan0 >> 3, t.z0 + 1, t.y + 1, t.x + 1);
     else if constexpr (MODE != EPI_CL16)
-        fbase = ep.out_f32 + ((size_t)t.n * ep.cout + t.chan0) * vol + ((size_t)t.z0 * Hh + t.y) * Ww + t.x;
+        fbase = ep.out_f32 + (size_t)t.n * ep.out_nstride + (size_t)t.chan0 * vol + ((size_t)t.z0 * Hh + t.y) * Ww + t.x;
     const int chunks = ncols >> 4;
     for (int cb = 0; cb < chunks; ++cb) {
         const int c0 = t.chan0 + cb * 16;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                 } else if constexpr (MODE == EPI_F32_HEAD) {
                     // 1x1x1 conv on the voxel's channel vector (registers) with the head in shared memory
                     const float *hb = seed + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
-                    float *o = ep.out_f32 + (size_t)t.n * ep.head_nc * vol + ((size_t)z * Hh + t.y) * Ww + t.x;
+                    float *o = ep.out_f32 + (size_t)t.n * ep.out_nstride + ((size_t)z * Hh + t.y) * Ww + t.x;
 #pragma unroll 2
                     for (int k = 0; k < ep.head_nc; ++k) {
                         float a = hb[k];
@@ -290,7 +290,7 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
                     }
                 } else {
                     // fused all-gather: the same values go to every rank's gather buffer over NVLink
-                    const size_t off = ((size_t)(ep.sample_offset + t.n) * ep.cout + c0) * vol +
+                    const size_t off = (size_t)(ep.sample_offset + t.n) * ep.out_nstride + (size_t)c0 * vol +
                                        ((size_t)z * Hh + t.y) * Ww + t.x;
                     for (int pr = 0; pr < ep.n_peers; ++pr) {
                         float *o = ep.out_peers[pr] + off;

@@ -231,6 +231,26 @@ class Engine:
                 self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream))
         return out
 
+    def forward_into(self, x: torch.Tensor, dest: torch.Tensor, channel_offset: int) -> torch.Tensor:
+        """Forward whose output lands in channels ``[channel_offset, channel_offset + C)`` of the wider contiguous
+        fp32 tensor ``dest`` ``[N, C_total, D, H, W]`` -- a zero-copy ``torch.cat`` with features the caller puts into
+        the other channels (anx_engine_forward_concat; reference instance_optimization.py:16-119 concatenates the
+        MIND-SSC descriptors in front of the network features)."""
+        x = x.contiguous().float()
+        n, _, d, h, w = x.shape
+        if dest.dim() != 5 or dest.shape[0] != n or tuple(dest.shape[2:]) != (d, h, w) or dest.dtype != torch.float32 \
+                or dest.device != self.device or not dest.is_contiguous() \
+                or not 0 <= channel_offset <= dest.shape[1] - self.output_nc:
+            raise ValueError(f"`dest` must be a contiguous fp32 [N, >= {channel_offset + self.output_nc}, D, H, W] tensor "
+                             f"on {self.device} matching the input's batch and spatial size")
+        ws = self.workspace(n, d, h, w)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_concat(
+                self._h, x.data_ptr(), dest.data_ptr(), dest.shape[1], channel_offset, n, d, h, w,
+                ws.data_ptr(), ws.numel(), stream))
+        return dest
+
     def forward_allgather(self, x: torch.Tensor, peer_ptrs, rank: int):
         """Forward whose last conv stores into every rank's gather buffer (see
         anx_engine_forward_allgather).  ``peer_ptrs``: device pointers (ints) of the

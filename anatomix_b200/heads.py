@@ -139,6 +139,47 @@ def scaled_features(unet: nn.Module, scale: float) -> nn.Module:
     return _ScaledUnet(unet, scale)
 
 
+def normalize_features(x: torch.Tensor, mode: str = "unit", eps: Optional[float] = None, inplace: bool = False) -> torch.Tensor:
+    """Voxelwise normalisation across channels of ``[N, C, D, H, W]`` features, as the reference prescribes for the dev
+    models before registration / visualisation (README.md:13,49): ``mode="unit"`` is
+    ``F.normalize(x, dim=1)`` (unit L2 norm), ``mode="zscore"`` is ``(x - x.mean(1, True)) / (x.std(1, keepdim=True) + eps)``.
+    fp32 CUDA tensors go through the engine library's streaming kernel (anx_channel_normalize_f32), anything else
+    through torch."""
+    if mode not in ("unit", "zscore"):
+        raise ValueError("mode is 'unit' or 'zscore'")
+    if eps is None:
+        eps = 1e-12 if mode == "unit" else 0.0
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 5 or (torch.is_grad_enabled() and x.requires_grad):
+        if mode == "unit":
+            return F.normalize(x, dim=1, eps=eps)
+        return (x - x.mean(1, keepdim=True)) / (x.std(1, keepdim=True) + eps)
+    lib = _lib.load()
+    x = x.contiguous()
+    n, c, d, h, w = x.shape
+    out = x if inplace else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        st = lib.anx_channel_normalize_f32(x.data_ptr(), out.data_ptr(), n, c, d, h, w, 0 if mode == "unit" else 1,
+                                           C.c_float(eps), torch.cuda.current_stream(x.device).cuda_stream)
+    if st != _lib.ANX_OK:
+        raise _lib.EngineError(st, "anx_channel_normalize_f32")
+    return out
+
+
+def features_behind(unet: nn.Module, x: torch.Tensor, front: torch.Tensor) -> torch.Tensor:
+    """``torch.cat([front, unet(x)], dim=1)`` without copying the network features: the engine writes them straight
+    behind the ``front`` channels of one buffer (reference instance_optimization.py:16-119:
+    ``torch.concatenate([mind_fixed, pred_fixed], dim=1)``).  Falls back to the plain concat off the engine path."""
+    import os
+    if os.environ.get("ANATOMIX_B200_DISABLE") == "1" or not hasattr(unet, "engine_ineligible_reason") \
+            or unet.engine_ineligible_reason(x) is not None or front.dtype != torch.float32 or front.device != x.device:
+        return torch.cat([front, unet(x)], dim=1)
+    eng = unet._engine_binding().engine_for(x.device)
+    n, cf = front.shape[0], front.shape[1]
+    dest = torch.empty((n, cf + eng.output_nc) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    dest[:, :cf].copy_(front)
+    return eng.forward_into(x, dest, cf)
+
+
 def avg_pool3d_scaled(x: torch.Tensor, k: int, scale: float = 1.0) -> torch.Tensor:
     """``scale * F.avg_pool3d(x, k, stride=k)`` for fp32 ``[N, C, D, H, W]``; CUDA tensors go through the
     engine library's streaming kernel, anything else through torch."""

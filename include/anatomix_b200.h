@@ -266,6 +266,22 @@ anx_status anx_engine_export_tap(anx_engine *engine, int32_t k, int32_t n, int32
                                  int32_t w, void *workspace, size_t workspace_bytes,
                                  float *out_ncdhw, void *stream);
 
+/* Zero-copy channel concat: the forward writes its output channels as channels [channel_offset, channel_offset + C)
+ * of a wider fp32 [N, dst_channels, D, H, W] tensor whose other channels the caller fills.  Replaces:
+ * `torch.concatenate([mind_fixed, pred_fixed], dim=1)` (MIND-SSC descriptors in front of the network features,
+ * anatomix/registration/instance_optimization.py:16-119): the 134 MB-per-volume feature tensor is not copied. */
+anx_status anx_engine_forward_concat(anx_engine *engine, const float *in_ncdhw, float *dst_ncdhw,
+                                     int32_t dst_channels, int32_t channel_offset,
+                                     int32_t n, int32_t d, int32_t h, int32_t w,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Voxelwise normalisation across the channels of a contiguous fp32 [n, channels, D, H, W] device tensor, in place
+ * allowed: mode 0 = unit L2 norm (x / max(||x||, eps)), mode 1 = zero mean / unit (unbiased) standard deviation
+ * ((x - mean) / (std + eps)).  Replaces: the per-voxel feature normalisation the reference prescribes for the dev
+ * models before registration / visualisation (README.md:13,49). */
+anx_status anx_channel_normalize_f32(const float *in, float *out, int64_t n, int32_t channels,
+                                     int32_t d, int32_t h, int32_t w, int32_t mode, float eps, void *stream);
+
 /* out = scale * avg_pool3d(in, k, stride=k) on a contiguous fp32 [nc, D, H, W] device tensor (floor
  * mode), on the current device.  Replaces: `pred * downscale_feat_scalar` followed by
  * `F.avg_pool3d(features, grid_sp, stride=grid_sp)`

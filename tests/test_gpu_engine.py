@@ -719,3 +719,35 @@ def test_open_slab_faces_are_left_to_the_neighbour(state_6m, cfgkw, shape):
         else:
             assert touched > 0
     eng.set_slab(False, False, 0)
+
+
+@pytest.mark.parametrize("shape,c", [((2, 16, 8, 12, 20), 16), ((1, 32, 4, 6, 10), 32), ((1, 5, 3, 3, 7), 5)])
+def test_voxelwise_channel_normalisation(shape, c):
+    """README.md:13,49 of the reference: unit norm or zero mean / unit std across channels, per voxel."""
+    import torch.nn.functional as F
+    from anatomix_b200.heads import normalize_features
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(8)) * 3 + 1
+    got = normalize_features(x.cuda(), "unit").cpu()
+    assert torch.allclose(got, F.normalize(x, dim=1), atol=1e-6, rtol=1e-5)
+    got = normalize_features(x.cuda(), "zscore").cpu()
+    want = (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-4)
+    y = x.cuda().clone()
+    assert normalize_features(y, "unit", inplace=True) is y and torch.allclose(y.cpu(), F.normalize(x, dim=1), atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 32, 32, 32), (1, 1, 32, 32, 128)])
+def test_zero_copy_concat_behind_other_features(state_6m, shape):
+    """instance_optimization.py:16-119: MIND-SSC descriptors (12 channels) in front of the network features."""
+    from anatomix_b200 import Unet
+    from anatomix_b200.heads import features_behind
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    x = rand_input(shape, 5).cuda()
+    front = torch.randn((shape[0], 12) + shape[2:], device="cuda")
+    with torch.no_grad():
+        got = features_behind(m, x, front)
+        want = torch.cat([front, m(x)], dim=1)
+    assert got.shape == want.shape and torch.equal(got, want)

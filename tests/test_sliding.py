@@ -71,3 +71,38 @@ def test_small_volume_is_padded_and_cropped():
     x = torch.rand(2, 1, 6, 8, 5)
     y = sliding_window_features(x, (8, 8, 8), 4, fn, overlap=0.5, mode="gaussian", sigma_scale=0.25)
     assert y.shape == (2, 1, 6, 8, 5) and torch.allclose(y, x + 1.0, atol=1e-6)
+
+
+def test_literal_fixture_of_the_monai_algorithm():
+    """Pin against numbers derived BY HAND from MONAI's published `sliding_window_inference` algorithm (MONAI itself is
+    not importable offline; reference call sites convex_adam_utils.py:202-219, train_segmentation.py:196-199), not
+    against this module's own helpers.
+
+    Image (4, 5, 6), window (2, 3, 4), overlap 0.5: scan interval per axis = int(roi * (1 - overlap)) = (1, 1, 2);
+    windows per axis = ceil((img - roi) / interval) + 1 = (3, 3, 2), the last one pulled back to end at the border.
+    Gaussian importance map, sigma = 0.25 * roi per axis, samples at -(n-1)/2 ... (n-1)/2:
+      n = 2, sigma 0.5 : exp(-0.25 / 0.5)    = 0.60653066 (both taps)
+      n = 3, sigma 0.75: exp(-1 / 1.125)     = 0.41111229, 1, 0.41111229
+      n = 4, sigma 1.0 : exp(-2.25 / 2)      = 0.32465247, exp(-0.25 / 2) = 0.88249690 (mirrored)
+    separable product, floored at max(min, 1e-3) = its own minimum 0.60653066 * 0.41111229 * 0.32465247 = 0.08095281."""
+    from anatomix_b200.sliding import importance_map, scan_intervals, window_starts
+    assert scan_intervals((4, 5, 6), (2, 3, 4), 0.5) == [1, 1, 2]
+    starts = window_starts((4, 5, 6), (2, 3, 4), [1, 1, 2])
+    assert starts == [(z, y, x) for z in (0, 1, 2) for y in (0, 1, 2) for x in (0, 2)]
+    w = importance_map((2, 3, 4), "gaussian", 0.25)
+    gz, gy, gx = [0.60653066, 0.60653066], [0.41111229, 1.0, 0.41111229], [0.32465247, 0.88249690, 0.88249690, 0.32465247]
+    want = torch.tensor([[[a * b * c for c in gx] for b in gy] for a in gz])
+    assert torch.allclose(w, want, atol=1e-7, rtol=1e-6) and abs(w.min().item() - 0.08095281) < 1e-7
+    # the registration setting (256^3 scan, 128^3 windows, overlap 0.8): interval int(128 * 0.2) = 25, seven
+    # windows per axis, the last pulled back from 150 to 128 -> 343 windows
+    assert scan_intervals((256,) * 3, (128,) * 3, 0.8) == [25, 25, 25]
+    s = window_starts((256,) * 3, (128,) * 3, [25, 25, 25])
+    assert len(s) == 343 and sorted({a for a, _, _ in s}) == [0, 25, 50, 75, 100, 125, 128]
+    # a window as large as the image along an axis: one window there, interval = the whole axis
+    assert scan_intervals((8, 6), (8, 3), 0.5) == [8, 1] and window_starts((8, 6), (8, 3), [8, 1]) == [(0, 0), (0, 1), (0, 2), (0, 3)]
+    # blended output of a constant predictor is that constant everywhere (weights normalise out), whatever the overlap
+    from anatomix_b200.sliding import sliding_window_features
+    x = torch.zeros(1, 1, 4, 5, 6)
+    y = sliding_window_features(x, (2, 3, 4), 3, lambda p: torch.full((p.shape[0], 2) + tuple(p.shape[2:]), 7.0), overlap=0.5,
+                                mode="gaussian", sigma_scale=0.25)
+    assert y.shape == (1, 2, 4, 5, 6) and torch.allclose(y, torch.full_like(y, 7.0), atol=1e-6)
