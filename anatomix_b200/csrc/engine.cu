@@ -436,6 +436,16 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     if (g.b_static && g.ncols == 16 && D >= 16 && !exp_env("ANX_NO_BZ16")) bz = 16;
     g.acc_stages = 2;
     bz = std::min(bz, D);
+    // Unfolded (wide) layers at the deep levels: a tile is a long serial chain of MMAs (27 taps x Cin / 16 per
+    // plane) and there are few tiles, so with two planes per tile most SMs idle while a few grind: one plane per
+    // tile doubles the parallelism at no extra MMA work (unfolded tiles have no z halo cost in the MMAs).  Only
+    // while the doubled tile count still fits one wave: every tile streams the layer's whole weight set from
+    // L2, so past one wave the extra weight traffic costs more than the parallelism brings (measured at batch 8:
+    // conv38 0.086 -> 0.110 ms with 256 tiles; at batch 2: 0.086 -> 0.060 ms with 64).
+    if (!c.fold && bz > 1 && !exp_env("ANX_NO_BZ1")) {
+        const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y) * ((D + bz - 1) / bz) * N * c.n_splits;
+        if (2 * tiles <= (size_t)e->num_sms) bz = 1;
+    }
     g.bz = bz;
     g.fuse_pool = (c.pool_dst_buf >= 0 && bz % 4 == 0) ? 1 : 0;
     int cols = g.acc_stages * bz * g.ncols;
