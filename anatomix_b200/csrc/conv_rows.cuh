@@ -39,6 +39,11 @@ constexpr int ROWS_B_TAP_BYTES = 2 * ROWS_N * 16;
 constexpr int ROWS_B_IMAGE_BYTES = 3 * ROWS_B_TAP_BYTES;        // three dx taps
 constexpr int ROWS_STRIP_COLS = ROWS_BY * 48;   // TMEM columns of one strip
 constexpr int ROWS_THREADS = 64 + 32 * 8;
+// Stem variant (C_in = 1, fp32 NCDHW input): four builder warps (thread = x voxel) write the A tiles, see below.
+constexpr int ROWS_STEM_THREADS = ROWS_THREADS + 128;
+constexpr int ROWS_STEM_TILE_BYTES = 2 * ROWS_X * 16;           // one input row: two K halves x 128 lanes x 16 B
+constexpr int ROWS_STEM_B_IMAGE_BYTES = 2 * ROWS_N * 16;        // one z rotation: all three dx taps live in K
+static_assert(ROWS_IN_Y * ROWS_STEM_TILE_BYTES <= ROWS_PLANE_BYTES, "a stem plane must fit a ring stage");
 
 struct RowsGeom {
     int N, D, H, W;
@@ -47,6 +52,7 @@ struct RowsGeom {
     int dt;
     uint32_t smem_bytes;
     uint32_t ablate;
+    int z_halo;              // stem variant: the input carries one extra plane at each end of D (depth-slab mode)
 };
 
 struct RowsShared {
@@ -59,9 +65,18 @@ struct RowsShared {
 };
 static_assert(offsetof(RowsShared, shift) % 16 == 0, "shift must be 16-byte aligned");
 
-template <int MODE>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 (also the fused gather), EPI_CL16 or EPI_F32_HEAD
-__global__ void __launch_bounds__(ROWS_THREADS, 1)
-conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep) {
+// STEM = true: the network's first conv (C_in = 1, reference network.py:309-326) in the same row form.  K = 16 of
+// ONE instruction holds the three dx taps of the hi / lo bf16 split of the fp32 input,
+//      A[x][k] = { hi(x-1), hi(x), hi(x+1),  lo(x-1), lo(x), lo(x+1),  hi(x-1), hi(x), hi(x+1),  0 ... }
+//      B[n][k] = { w_hi(dx = 0, 1, 2),       w_hi(0, 1, 2),            w_lo(0, 1, 2),            0 ... }
+// (x_hi w_hi + x_lo w_hi + x_hi w_lo: fp32-level accuracy, the dropped x_lo w_lo term is 2^-16 relative), so one
+// N = 144 MMA per input row replaces the three dx instructions of the 16-channel layers.  Four builder warps
+// (thread = x voxel) read the fp32 rows straight from global memory (reflect padding by index arithmetic) and write
+// the canonical K-major A tiles into the plane ring; MMA issue, TMEM layout and epilogue are the shared code.
+template <int MODE, bool STEM = false>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 (also the fused gather), EPI_CL16 or EPI_F32_HEAD
+__global__ void __launch_bounds__(STEM ? ROWS_STEM_THREADS : ROWS_THREADS, 1)
+conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep,
+                  const float *__restrict__ stem_in) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_ring = smem;
     uint8_t *b_img = a_ring + (size_t)ROWS_STAGES * ROWS_PLANE_BYTES;
@@ -72,7 +87,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
     const int planes = g.zs + 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], 1); mbar_init(&sh->empty_a[i], 1); }
+        for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], STEM ? 128 : 1); mbar_init(&sh->empty_a[i], 1); }
         mbar_init(&sh->full_b, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_ready[i], 1); mbar_init(&sh->drained[i], 8); }
         fence_barrier_init();
@@ -100,13 +115,15 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         z0 = tz * g.zs;
     };
 
+    constexpr uint32_t B_BYTES = STEM ? 3 * ROWS_STEM_B_IMAGE_BYTES : 3 * ROWS_B_IMAGE_BYTES;
     if (warp == 0) {
         // ------------------------------------------------------------ producer
         if (lane == 0 && blockIdx.x < g.total_units) {
-            mbar_arrive_expect_tx(&sh->full_b, 3 * ROWS_B_IMAGE_BYTES);
-            bulk_load_1d(b_img, wrows, 3 * ROWS_B_IMAGE_BYTES, &sh->full_b);
+            mbar_arrive_expect_tx(&sh->full_b, B_BYTES);
+            bulk_load_1d(b_img, wrows, B_BYTES, &sh->full_b);
         }
         uint32_t ka = 0;
+        if constexpr (!STEM)
         for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
             int n, x0, y0, z0;
             decode(unit, n, x0, y0, z0);
@@ -128,21 +145,67 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
             }
         }
         __syncwarp();
+    } else if (STEM && warp >= 10) {
+        // ------------------------------------------------- stem: A-tile builders
+        const int bx = threadIdx.x - ROWS_THREADS;            // x voxel of the 128-wide tile
+        const int Dd = g.D, Hh = g.H, Ww = g.W;
+        auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+        uint32_t ka = 0;
+        for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+            int n, x0, y0, z0;
+            decode(unit, n, x0, y0, z0);
+            const int x = x0 + bx;
+            const int xm = refl(x - 1, Ww), xp = refl(x + 1, Ww);
+            for (int p = 0; p < planes; ++p, ++ka) {
+                const uint32_t st = ka % ROWS_STAGES;
+                // input plane z0 - 1 + p: reflect at the global faces, or the attached neighbour planes (z_halo)
+                const int zi = g.z_halo ? z0 + p : refl(z0 - 1 + p, Dd);
+                const float *pl = stem_in + ((size_t)n * (Dd + 2 * g.z_halo) + zi) * ((size_t)Hh * Ww);
+                float v[ROWS_IN_Y][3];
+#pragma unroll
+                for (int i = 0; i < ROWS_IN_Y; ++i) {           // all loads of the plane in flight before the slot wait
+                    const float *row = pl + (size_t)refl(y0 - 1 + i, Hh) * Ww;
+                    v[i][0] = __ldg(row + xm);
+                    v[i][1] = __ldg(row + x);
+                    v[i][2] = __ldg(row + xp);
+                }
+                mbar_wait(&sh->empty_a[st], ((ka / ROWS_STAGES) & 1) ^ 1, 26);
+                uint8_t *tile = a_ring + (size_t)st * ROWS_PLANE_BYTES + (size_t)bx * 16;
+#pragma unroll
+                for (int i = 0; i < ROWS_IN_Y; ++i) {
+                    // bf16 hi / lo split of the three taps: hi = rn(x), lo = rn(x - hi)
+                    uint32_t h01, l01, h2z, l2z;
+                    split_hi_lo(v[i][0], v[i][1], h01, l01);
+                    split_hi_lo(v[i][2], 0.0f, h2z, l2z);
+                    const uint32_t h2 = h2z & 0xffffu, l0 = l01 & 0xffffu, l1 = l01 >> 16, l2 = l2z & 0xffffu;
+                    // K = { hi0 hi1 | hi2 lo0 | lo1 lo2 | hi0 hi1 }  { hi2 0 | 0 0 | 0 0 | 0 0 }
+                    *reinterpret_cast<uint4 *>(tile + (size_t)i * ROWS_STEM_TILE_BYTES) =
+                        make_uint4(h01, h2 | (l0 << 16), l1 | (l2 << 16), h01);
+                    *reinterpret_cast<uint4 *>(tile + (size_t)i * ROWS_STEM_TILE_BYTES + ROWS_X * 16) = make_uint4(h2, 0u, 0u, 0u);
+                }
+                fence_proxy_async();          // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(&sh->full_a[st]);
+            }
+        }
     } else if (warp == 1) {
         // ---------------------------------------------- MMA issuer (warp-uniform)
         uint32_t ka = 0;
         const uint32_t hi_bits = (128u >> 4) | (1u << 14);                   // SBO = 128 B for A and B
-        const uint32_t a_lbo = ((uint32_t)(ROWS_GROUP_BYTES >> 4) & 0x3FFF) << 16;
+        const uint32_t a_lbo = ((uint32_t)((STEM ? ROWS_X * 16 : ROWS_GROUP_BYTES) >> 4) & 0x3FFF) << 16;
         const uint32_t b_lbo = ((uint32_t)ROWS_N & 0x3FFF) << 16;            // 16 * 144 bytes between the K halves
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t b0 = (smem_u32(b_img) & 0x3FFFF) >> 4;
+        constexpr uint32_t A_ROW16 = (STEM ? ROWS_STEM_TILE_BYTES : ROWS_ROW_BYTES) >> 4;          // 16-byte units per input row
+        constexpr uint32_t B_IMG16 = (STEM ? ROWS_STEM_B_IMAGE_BYTES : ROWS_B_IMAGE_BYTES) >> 4;
+        const int mma_dt = STEM ? (int)DT_BF16 : g.dt;                       // the stem's operands are always bf16 hi / lo pairs
         mbar_wait_warp(&sh->full_b, 0, 22);
         for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
             for (int p = 0; p < planes; ++p, ++ka) {
                 const uint32_t st = ka % ROWS_STAGES;
                 mbar_wait_warp(&sh->full_a[st], (ka / ROWS_STAGES) & 1, 23);
+                if constexpr (STEM) tc_fence_after();
                 const uint32_t a0 = (smem_u32(a_ring + (size_t)st * ROWS_PLANE_BYTES) & 0x3FFFF) >> 4;
-                const uint32_t bimg = b0 + (uint32_t)(p % 3) * (ROWS_B_IMAGE_BYTES >> 4);
+                const uint32_t bimg = b0 + (uint32_t)(p % 3) * B_IMG16;
                 for (int s = 0; s < 2; ++s) {
                     mbar_wait_warp(&sh->drained[s], ka & 1, 24);   // the slot this plane touches first is re-seeded
                     tc_fence_after();
@@ -152,14 +215,18 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                             const int yo_min = i - 2 > 0 ? i - 2 : 0;
                             const int yo_max = i < ROWS_BY - 1 ? i : ROWS_BY - 1;
                             const uint32_t nrows = (uint32_t)(yo_max - yo_min + 1);
-                            const uint32_t idesc = idesc_m128(nrows * 48u, g.dt);
+                            const uint32_t idesc = idesc_m128(nrows * 48u, mma_dt);
                             const uint32_t dcol = tmem_u + (uint32_t)s * ROWS_STRIP_COLS + (uint32_t)yo_min * 48u;
-                            const uint32_t arow = a0 + (uint32_t)(s * ROWS_BY + i) * (ROWS_ROW_BYTES >> 4);
+                            const uint32_t arow = a0 + (uint32_t)(s * ROWS_BY + i) * A_ROW16;
                             const uint32_t brow = bimg + (uint32_t)(2 - (i - yo_min)) * 48u;   // 16 B per B row
+                            if constexpr (STEM) {
+                                umma_bf16_warp(dcol, make_desc(hi_bits, arow | a_lbo), make_desc(hi_bits, brow | b_lbo), idesc);
+                            } else {
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx)
-                                umma_bf16_warp(dcol, make_desc(hi_bits, (arow + dx) | a_lbo),
-                                               make_desc(hi_bits, (brow + dx * (ROWS_B_TAP_BYTES >> 4)) | b_lbo), idesc);
+                                for (int dx = 0; dx < 3; ++dx)
+                                    umma_bf16_warp(dcol, make_desc(hi_bits, (arow + dx) | a_lbo),
+                                                   make_desc(hi_bits, (brow + dx * (ROWS_B_TAP_BYTES >> 4)) | b_lbo), idesc);
+                            }
                         }
                     }
                     umma_commit_warp(&sh->acc_ready[s]);
@@ -179,6 +246,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         const int lx = q * 32 + lane;
         const int Dd = g.D, Hh = g.H, Ww = g.W;
         const size_t vol = (size_t)Dd * Hh * Ww;
+        // loop invariants of the padded stores: row / plane / group strides (uint4 units), shell semantics
+        const size_t rowp = (size_t)ep.dst.pitch, plane = rowp * (Hh + 2), gstride = plane * (Dd + 2);
+        const int rep = ep.dst.shell_rep, zopen = ep.dst.z_open;
         float sd[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) sd[i] = SEEDED ? 0.0f : sh->shift[i];
@@ -256,6 +326,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
             int n, x0, y0, z0;
             decode(unit, n, x0, y0, z0);
             const int x = x0 + lx;
+            const int mdx = mirror_delta(x, Ww, rep);              // this lane's x never changes within a unit
+            // fp32 outputs: this lane's column of the unit's sample (one pointer per unit, rows add an offset)
+            const size_t out_off = (size_t)(ep.sample_offset + n) * ep.out_nstride + (size_t)x;
             const int next_unit = unit + (int)gridDim.x;
             const bool nvalid = next_unit < g.total_units;
             int nn = 0, nx0 = 0, ny0 = 0, nz0 = 0;
@@ -264,6 +337,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                 const int o = p - 2;                               // output plane completed by input plane p
                 const int slot = (o + 3) % 3;
                 const int z = z0 + o;
+                const int mdz = mirror_delta_z(z, Dd, rep, zopen);  // one plane per drain: uniform over the warp
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     // seeds of the plane that uses this slot next: o + 3 of this unit, or plane 0 of the next unit
@@ -305,13 +379,10 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                                 for (int i = 0; i < 8; ++i) pm[i] = r == 0 ? pk[i] : max16x2(pm[i], pk[i], ep.dt);
                             }
                             if (ANX_ABL(g, 2)) continue;
-                            const size_t rowp = (size_t)ep.dst.pitch, plane = rowp * (Hh + 2), gstride = plane * (Dd + 2);
                             uint4 *pd = ep.dst.at(n, 0, z + 1, y + 1, x + 1);
                             *pd = q0;
                             pd[gstride] = q1;
-                            const int rep = ep.dst.shell_rep;
-                            const int mdx = mirror_delta(x, Ww, rep), mdy = mirror_delta(y, Hh, rep),
-                                      mdz = mirror_delta_z(z, Dd, rep, ep.dst.z_open);
+                            const int mdy = mirror_delta(y, Hh, rep);
                             if (mdx | mdy | mdz) {
                                 store_mirrors(pd, q0, mdz, mdy, mdx, rowp, plane);
                                 store_mirrors(pd + gstride, q1, mdz, mdy, mdx, rowp, plane);
@@ -320,13 +391,23 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                             if (ANX_ABL(g, 2)) continue;
                             // fp32 NCDHW: a warp writes one 128-byte run per channel; with a fused feature
                             // all-gather the same runs go to every rank's gather buffer over NVLink
-                            const size_t off = (size_t)(ep.sample_offset + n) * ep.out_nstride + ((size_t)z * Hh + y) * Ww + x;
-                            const int targets = ep.n_peers > 0 ? ep.n_peers : 1;
-                            for (int pr = 0; pr < targets; ++pr) {
-                                float *po = (ep.n_peers > 0 ? ep.out_peers[pr] : ep.out_f32) + off;
+                            const size_t off = out_off + ((size_t)z * Hh + y) * Ww;
+                            if (ep.n_peers == 0) {
+                                float *po = ep.out_f32 + off;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (i < ep.cout) po[(size_t)i * vol] = v[i];
+                                for (int i = 0; i < 16; ++i) {
+                                    if (i < ep.cout) *po = v[i];
+                                    po += vol;
+                                }
+                            } else {
+                                for (int pr = 0; pr < ep.n_peers; ++pr) {
+                                    float *po = ep.out_peers[pr] + off;
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        if (i < ep.cout) *po = v[i];
+                                        po += vol;
+                                    }
+                                }
                             }
                         } else if constexpr (MODE == EPI_CL16) {
                             if (ANX_ABL(g, 2)) continue;
@@ -342,7 +423,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                         } else {
                             if (ANX_ABL(g, 2)) continue;
                             const float *hb = sh->shift + HEAD_SMEM_OFFSET, *hw = hb + HEAD_MAX;
-                            float *po = ep.out_f32 + (size_t)n * ep.out_nstride + ((size_t)z * Hh + y) * Ww + x;
+                            float *po = ep.out_f32 + out_off + ((size_t)z * Hh + y) * Ww;
 #pragma unroll 2
                             for (int k = 0; k < ep.head_nc; ++k) {
                                 float a = hb[k];

@@ -106,6 +106,7 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
     void *d_wrows = nullptr;  // 16 -> 16 row kernel: three B images [z rotation][dx][k half][144 rows][8] (conv_rows.cuh)
+    void *d_wstem_rows = nullptr;   // row-form stem (Cin = 1, 16 columns): three bf16 B images [z rotation][k half][144 rows][8]
     float *d_bias = nullptr;  // [ncols]
     size_t wpack_bytes = 0;
 };
@@ -641,6 +642,24 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const ConvLayer &c = e->convs[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out);
         const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
+        if (!force_simt && e->use_rows && c.d_wstem_rows && !ep.stats && p.W % ROWS_X == 0 && p.H % ROWS_YB == 0 &&
+            p.D % 16 == 0 && !exp_env("ANX_NO_STEM_ROWS")) {
+            // row-form stem: the 16 -> 16 row kernel's pipeline with builder warps in front of it
+            RowsGeom rg{};
+            rg.N = p.N; rg.D = p.D; rg.H = p.H; rg.W = p.W;
+            rg.zs = 16;
+            rg.tiles_x = p.W / ROWS_X; rg.tiles_y = p.H / ROWS_YB; rg.tiles_z = p.D / rg.zs;
+            rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
+            rg.total_units = rg.units_per_sample * p.N;
+            rg.dt = e->dt;
+            rg.z_halo = zh0;
+            if (const char *ab = exp_env("ANX_ABLATE")) rg.ablate = (uint32_t)atoi(ab);
+            rg.smem_bytes = (uint32_t)(ROWS_STAGES * ROWS_PLANE_BYTES + 3 * ROWS_B_IMAGE_BYTES + sizeof(RowsShared));
+            const int grid = std::min(rg.total_units, e->num_sms);
+            conv3_rows_kernel<EPI_PADDED, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
+                ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
+            break;
+        }
         if (!force_simt && c.d_wstem && p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
             !exp_env("ANX_SIMT_STEM")) {
             // tensor-core stem: per-call tensor map over the caller's fp32 input
@@ -728,7 +747,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const ActView src = view_of(e, p, c.src_buf, 0);
             const int grid = std::min(rg.total_units, e->num_sms);
             const uint8_t *wr = (const uint8_t *)c.d_wrows;
-#define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep)
+#define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep, nullptr)
             if (ep.mode == OUT_NCDHW_F32) {
                 if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD);
                 else if (ep.cl16) ANX_ROWS_LAUNCH(EPI_CL16);
@@ -888,7 +907,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     ANX_SMEM(conv3_umma_kernel<EPI_PADDED>); ANX_SMEM(conv3_umma_kernel<EPI_POOL>); ANX_SMEM(conv3_umma_kernel<EPI_D2S>);
     ANX_SMEM(conv3_umma_kernel<EPI_STATS>); ANX_SMEM(conv3_umma_kernel<EPI_F32>); ANX_SMEM(conv3_umma_kernel<EPI_F32_PEERS>);
     ANX_SMEM(conv3_umma_kernel<EPI_SEEDED>); ANX_SMEM(conv3_umma_kernel<EPI_F32_HEAD>); ANX_SMEM(conv3_umma_kernel<EPI_CL16>);
-    ANX_SMEM(conv3_rows_kernel<EPI_CL16>);
+    ANX_SMEM(conv3_rows_kernel<EPI_CL16>); ANX_SMEM((conv3_rows_kernel<EPI_PADDED, true>));
     ANX_SMEM(conv3_rows_kernel<EPI_PADDED>); ANX_SMEM(conv3_rows_kernel<EPI_F32>); ANX_SMEM(conv3_rows_kernel<EPI_F32_HEAD>);
     ANX_SMEM(conv3_rows_kernel<EPI_SEEDED>); ANX_SMEM(conv3_rows_kernel<EPI_POOL>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
@@ -924,6 +943,7 @@ void anx_engine_destroy(anx_engine *e) {
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
+        if (c.d_wstem_rows) cudaFree(c.d_wstem_rows);
         if (c.d_wrows) cudaFree(c.d_wrows);
         if (c.d_bias) cudaFree(c.d_bias);
     }
@@ -981,6 +1001,35 @@ static anx_status upload_conv(anx_engine *e, ConvLayer &c, const std::vector<flo
             if (c.d_wstem) { cudaFree(c.d_wstem); c.d_wstem = nullptr; }
             ANX_CUDA(e, cudaMalloc(&c.d_wstem, img.size() * 2));
             ANX_CUDA(e, cudaMemcpy(c.d_wstem, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        }
+        if (c.d_wstem_rows) { cudaFree(c.d_wstem_rows); c.d_wstem_rows = nullptr; }
+        if (c.cin == 1 && c.ncols == 16) {
+            // row-form stem (conv3_rows_kernel<.., true>): image r (= input plane mod 3), row (j*3 + s)*16 + co holds
+            // the taps ky = 2 - j, kz = (r - s) mod 3 of output channel co; K = { w_hi(dx 0..2), w_hi(dx 0..2),
+            // w_lo(dx 0..2), 0 x 7 } against A = { x_hi, x_lo, x_hi } of the three dx neighbours
+            std::vector<uint16_t> img((size_t)3 * ROWS_STEM_B_IMAGE_BYTES / 2, 0);
+            for (int r = 0; r < 3; ++r)
+                for (int j = 0; j < 3; ++j)
+                    for (int s = 0; s < 3; ++s) {
+                        const int ky = 2 - j, kz = (r - s + 3) % 3;
+                        for (int o = 0; o < c.cout; ++o)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const float v = w[(size_t)o * 27 + kz * 9 + ky * 3 + dx];
+                                const uint16_t hi = f32_to_bf16_rne(v);
+                                uint32_t hb32 = (uint32_t)hi << 16;
+                                float hf;
+                                std::memcpy(&hf, &hb32, 4);
+                                const uint16_t lo = f32_to_bf16_rne(v - hf);
+                                const size_t row = (size_t)(j * 3 + s) * 16 + o;
+                                const uint16_t vals[3] = {hi, hi, lo};
+                                for (int part = 0; part < 3; ++part) {
+                                    const int k = part * 3 + dx;
+                                    img[(size_t)r * (ROWS_STEM_B_IMAGE_BYTES / 2) + ((size_t)(k / 8) * ROWS_N + row) * 8 + k % 8] = vals[part];
+                                }
+                            }
+                    }
+            ANX_CUDA(e, cudaMalloc(&c.d_wstem_rows, img.size() * 2));
+            ANX_CUDA(e, cudaMemcpy(c.d_wstem_rows, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
         }
     } else {
         // 16-bit slabs [split][chunk][group][tap(ky,kx)][kchunk][row][8]; folded rows = (dz=+1 | 0 | -1) x ncols

@@ -16,6 +16,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// hi/lo split of two fp32 values into packed bf16 pairs: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split_hi_lo(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
 // 8 floats -> 16 bytes of the storage type (round to nearest even)
 __device__ __forceinline__ uint4 pack_x8(const float *v, int dt) {
     if (dt == DT_BF16)

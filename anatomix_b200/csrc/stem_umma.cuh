@@ -71,12 +71,6 @@ __device__ __forceinline__ int brick_reflect(int i, int lo, int hi) {   // lo/hi
     return i < lo ? 2 * lo - i : (i > hi ? 2 * hi - i : i);
 }
 
-// hi/lo split of two fp32 values into packed bf16 pairs: hi = rn(x), lo = rn(x - hi)
-__device__ __forceinline__ void split_hi_lo(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-    hi = pack_bf16x2(x0, x1);
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-    lo = pack_bf16x2(x0 - h0, x1 - h1);
-}
 
 template <int KQ, int MODE>   // K chunks of 16 (1 for Cin = 1, 2 for Cin = 2..3, 3 for Cin = 4); EpiMode
 __global__ void __launch_bounds__(STEM_THREADS, 1)
