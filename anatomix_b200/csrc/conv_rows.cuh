@@ -58,7 +58,7 @@ struct RowsGeom {
 struct RowsShared {
     uint64_t full_a[ROWS_STAGES], empty_a[ROWS_STAGES];
     uint64_t full_b;
-    uint64_t acc_ready[2], drained[2];
+    uint64_t acc_ready[2][2], drained[2][2];   // [strip][row pair]: hand-over at half-strip granularity
     uint32_t tmem_slot;
     uint32_t pad[5];         // keeps `shift` 16-byte aligned (float4 reads of the head weights)
     float shift[16 + HEAD_FLOATS + 16];
@@ -89,7 +89,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
     if (threadIdx.x == 0) {
         for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], STEM ? 128 : 1); mbar_init(&sh->empty_a[i], 1); }
         mbar_init(&sh->full_b, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_ready[i], 1); mbar_init(&sh->drained[i], 8); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&sh->acc_ready[i >> 1][i & 1], 1); mbar_init(&sh->drained[i >> 1][i & 1], 4); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -207,11 +207,17 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                 const uint32_t a0 = (smem_u32(a_ring + (size_t)st * ROWS_PLANE_BYTES) & 0x3FFFF) >> 4;
                 const uint32_t bimg = b0 + (uint32_t)(p % 3) * B_IMG16;
                 for (int s = 0; s < 2; ++s) {
-                    mbar_wait_warp(&sh->drained[s], ka & 1, 24);   // the slot this plane touches first is re-seeded
-                    tc_fence_after();
-                    if (!(ANX_ABL(g, 1))) {
+                    // Hand-over with the epilogue per ROW PAIR of the strip: output rows {0, 1} are complete after
+                    // input row 3 and are drained (and re-seeded) while input rows 4, 5 still accumulate into rows
+                    // {2, 3}; the next plane's rows 0, 1 only need pair 0 drained.  Twice the pipeline depth of a
+                    // whole-strip hand-over for the same TMEM.
 #pragma unroll
-                        for (int i = 0; i < ROWS_BY + 2; ++i) {
+                    for (int i = 0; i < ROWS_BY + 2; ++i) {
+                        if (i == 0 || i == 2) {                     // input rows 0, 1 touch pair 0 only; row 2 is the first to touch pair 1
+                            mbar_wait_warp(&sh->drained[s][i >> 1], ka & 1, 24);
+                            tc_fence_after();
+                        }
+                        if (!(ANX_ABL(g, 1))) {
                             const int yo_min = i - 2 > 0 ? i - 2 : 0;
                             const int yo_max = i < ROWS_BY - 1 ? i : ROWS_BY - 1;
                             const uint32_t nrows = (uint32_t)(yo_max - yo_min + 1);
@@ -228,8 +234,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                                                    make_desc(hi_bits, (brow + dx * (ROWS_B_TAP_BYTES >> 4)) | b_lbo), idesc);
                             }
                         }
+                        if (i == 3) umma_commit_warp(&sh->acc_ready[s][0]);      // rows 0, 1 of the strip have all their taps
                     }
-                    umma_commit_warp(&sh->acc_ready[s]);
+                    umma_commit_warp(&sh->acc_ready[s][1]);
                 }
                 umma_commit_warp(&sh->empty_a[st]);
             }
@@ -292,7 +299,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&sh->drained[0]); mbar_arrive(&sh->drained[1]); }
+        if (lane == 0) { mbar_arrive(&sh->drained[0][h]); mbar_arrive(&sh->drained[1][h]); }
 
         uint32_t held[2][8];                        // POOL: row-pair maxima of the even plane of a z pair, per strip
 #pragma unroll
@@ -350,7 +357,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                         else if (p + 1 < planes) seeds_for(p + 1, 0, n, x0, y0, z0, nvalid, nn, nx0, ny0, nz0, nsq);
                         else if (nvalid) seeds_for(0, 0, nn, nx0, ny0, nz0, false, 0, 0, 0, 0, nsq);
                     }
-                    mbar_wait(&sh->acc_ready[s], ka & 1, 25);
+                    mbar_wait(&sh->acc_ready[s][h], ka & 1, 25);
                     tc_fence_after();
                     uint32_t pm[8];                                // POOL: maximum over this warp's two rows
 #pragma unroll
@@ -471,7 +478,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh->drained[s]);
+                    if (lane == 0) mbar_arrive(&sh->drained[s][h]);
                 }
             }
         }

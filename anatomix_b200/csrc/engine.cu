@@ -796,6 +796,13 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
         if (e->desc.interp_kind == ANX_INTERP_NEAREST)
             upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
+        else if (dst.D >= 4 && dst.H >= 4 && dst.W >= 32 && dst.D <= 65535 && (size_t)p.N * s.groups <= 65535) {
+            const dim3 grid(dst.H, dst.D, p.N * s.groups);
+            if (e->dt == DT_BF16)
+                upsample2_tri_grid_kernel<DT_BF16><<<grid, 128, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+            else
+                upsample2_tri_grid_kernel<DT_FP16><<<grid, 128, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+        }
         else
             upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(
                 src, dst, p.N, s.groups, e->desc.interp_kind, e->dt, e->slab_lower, e->slab_upper);

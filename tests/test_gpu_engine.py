@@ -47,10 +47,12 @@ def check_against_oracle(cfg, state, x, y_gpu, tight=True, upconv=True):
     assert torch.isfinite(got).all()
     r, c = rel_l2(got, want), min_cosine(got, want)
     assert r <= LOOSE_REL and c >= LOOSE_COS, f"loose gate: rel-L2 {r:.3e}, min cosine {c:.5f}"
+    rt = float("nan")
     if tight:
         emu = O.unet_forward(cfg, state, x, engine_rounding=True, emulate_upconv=upconv)
         rt = rel_l2(got, emu)
         assert rt <= TIGHT_REL, f"tight gate: rel-L2 {rt:.3e} vs bf16-emulating oracle"
+    print(f"PARITY shape {tuple(x.shape)} loose rel-L2 {r:.3e} cos {c:.5f} tight rel-L2 {rt:.3e}")
     return r, c
 
 
