@@ -26,6 +26,7 @@ FLAG_STORE_BF16 = 4
 FLAG_DEPTH_HALO_INPUT = 8
 FLAG_NO_UPCONV = 16
 FLAG_NO_ROWS = 32
+FLAG_NO_WS_REUSE = 64
 PAYLOAD_F32_NCDHW = 0
 PAYLOAD_CL16 = 1
 

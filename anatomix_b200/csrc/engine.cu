@@ -114,6 +114,7 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
 struct Buffer {               // padded planar activation buffer
     int level, groups;
     int shell_rep = 0;        // producer writes replicate instead of reflect copies into the shell
+    int first = -1, last = -1;   // first step that writes it, last step that touches it (workspace liveness)
 };
 
 // One nn.Conv3d of the reference's Sequential as the binding sees it (anx_engine_set_conv ordinal).
@@ -271,7 +272,12 @@ void build_program(anx_engine *e) {
     int mi = 0;
     std::vector<int> cat(nd), width(nd + 1);
     for (int i = 0; i <= nd; ++i) width[i] = g << i;
-    for (int i = 0; i < nd; ++i) cat[i] = add_buffer(e, i, 3 * width[i]);
+    // (see below) decoder level 0 behind a nearest upsample never materialises the upsampled tensor
+    const bool use_upconv = d.interp_kind == ANX_INTERP_NEAREST && d.norm_kind != ANX_NORM_INSTANCE &&
+                            !(d.flags & (ANX_FLAG_FORCE_SIMT | ANX_FLAG_NO_UPCONV)) && width[0] == 16 &&
+                            !exp_env("ANX_NO_UPCONV");   // the seeded skip conv handles one 16-channel chunk
+    // concat buffers [skip | upsampled]; with the low-resolution decoder conv the level-0 one holds the skip only
+    for (int i = 0; i < nd; ++i) cat[i] = add_buffer(e, i, (i == 0 && use_upconv) ? width[0] : 3 * width[i]);
 
     int cur = add_buffer(e, 0, g);
     add_conv(e, mi, d.input_nc, g, 0, false, true, -1, cur, 0);
@@ -308,9 +314,6 @@ void build_program(anx_engine *e) {
     // padding of the upsampled tensor equals replicate padding of L).  That launch runs with N = 8*w per A
     // tile instead of 3*w, never materialises the upsampled tensor, and stores its (shift-seeded) result
     // depth-to-space as 16-bit partial sums, which then seed the accumulators of the w -> w skip conv.
-    const bool use_upconv = d.interp_kind == ANX_INTERP_NEAREST && d.norm_kind != ANX_NORM_INSTANCE &&
-                            !(d.flags & (ANX_FLAG_FORCE_SIMT | ANX_FLAG_NO_UPCONV)) && width[0] == 16 &&
-                            !exp_env("ANX_NO_UPCONV");   // the seeded skip conv handles one 16-channel chunk
     std::vector<std::pair<int, int>> pairs;
     for (int l = nd - 1; l >= 0; --l) {
         if (use_upconv && l == 0) {
@@ -405,6 +408,29 @@ void build_taps(anx_engine *e) {
     }
 }
 
+// First writer / last user of every buffer over the launch sequence.
+void build_liveness(anx_engine *e) {
+    auto touch = [&](int buf, int step) {
+        if (buf < 0) return;
+        Buffer &b = e->bufs[buf];
+        if (b.first < 0) b.first = step;
+        b.last = std::max(b.last, step);
+    };
+    for (int si = 0; si < (int)e->steps.size(); ++si) {
+        const Step &s = e->steps[si];
+        if (s.kind == STEP_STEM || s.kind == STEP_CONV) {
+            const ConvLayer &c = e->convs[s.conv];
+            touch(c.src_buf, si);
+            touch(c.seed_buf, si);
+            touch(c.dst_buf, si);
+            touch(c.pool_dst_buf, si);        // written here when the pooling is fused into this conv's epilogue
+        } else {
+            touch(s.src_buf, si);
+            touch(s.dst_buf, si);
+        }
+    }
+}
+
 bool shape_ok(const anx_engine *e, int n, int d, int h, int w) {
     const int unit = 1 << e->desc.num_downs;
     if (n < 1 || d < 2 * unit || h < 2 * unit || w < 2 * unit) return false;
@@ -414,6 +440,47 @@ bool shape_ok(const anx_engine *e, int n, int d, int h, int w) {
 size_t buffer_bytes(const anx_engine *e, const Buffer &b, int n, int d, int h, int w) {
     const size_t dp = (d >> b.level) + 2, hp = (h >> b.level) + 2, wp = layout_of(w >> b.level, e->x_lead).pitch;
     return align_up((size_t)n * b.groups * dp * hp * wp * 16, 256);
+}
+
+// Byte offset of every activation buffer inside the workspace; returns the bytes they span.  Buffers whose lifetimes
+// (first writer .. last user) do not overlap share memory: placed largest first, each at the lowest offset where it
+// collides with no already-placed buffer that is live at the same time.  Engines in depth-slab mode keep one
+// region per buffer (a neighbour's halo plane may arrive while this rank is still several launches behind), as do
+// engines created with ANX_FLAG_NO_WS_REUSE (debugging: every intermediate tensor survives the forward).
+size_t plan_offsets(const anx_engine *e, int n, int d, int h, int w, std::vector<size_t> &off) {
+    const size_t nb = e->bufs.size();
+    off.assign(nb, 0);
+    std::vector<size_t> bytes(nb);
+    for (size_t i = 0; i < nb; ++i) bytes[i] = buffer_bytes(e, e->bufs[i], n, d, h, w);
+    size_t total = 0;
+    if (e->desc.flags & (ANX_FLAG_DEPTH_HALO_INPUT | ANX_FLAG_NO_WS_REUSE)) {
+        for (size_t i = 0; i < nb; ++i) { off[i] = total; total += bytes[i]; }
+        return total;
+    }
+    std::vector<size_t> order(nb);
+    for (size_t i = 0; i < nb; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return bytes[a] > bytes[b]; });
+    std::vector<size_t> placed;
+    for (size_t k : order) {
+        const Buffer &bk = e->bufs[k];
+        size_t at = 0;
+        bool moved = true;
+        while (moved) {                                   // lowest offset free of live neighbours
+            moved = false;
+            for (size_t j : placed) {
+                const Buffer &bj = e->bufs[j];
+                const bool live_together = !(bk.last < bj.first || bj.last < bk.first);
+                if (live_together && at < off[j] + bytes[j] && off[j] < at + bytes[k]) {
+                    at = off[j] + bytes[j];
+                    moved = true;
+                }
+            }
+        }
+        off[k] = at;
+        placed.push_back(k);
+        total = std::max(total, at + bytes[k]);
+    }
+    return total;
 }
 
 // Tile / pipeline configuration of one tensor-core conv at one shape.
@@ -523,11 +590,7 @@ anx_status get_plan(anx_engine *e, int N, int D, int H, int W, void *workspace, 
     auto p = std::make_shared<ShapePlan>();
     p->N = N; p->D = D; p->H = H; p->W = W;
     p->workspace = workspace;
-    size_t off = 0;
-    for (auto &b : e->bufs) {
-        p->buf_offset.push_back(off);
-        off += buffer_bytes(e, b, N, D, H, W);
-    }
+    size_t off = plan_offsets(e, N, D, H, W, p->buf_offset);
     p->stats_offset = off;
     p->conv_stats_offset.assign(e->convs.size(), 0);
     for (size_t i = 0; i < e->convs.size(); ++i)
@@ -905,6 +968,7 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     if (const char *rw = exp_env("ANX_ROWS")) e->use_rows = atoi(rw);
     build_program(e);
     build_taps(e);
+    build_liveness(e);
     for (auto &c : e->convs) {
         c.fold = (!c.is_stem && c.n_splits == 1 && 3 * c.ncols <= 256 && !exp_env("ANX_NOFOLD")) ? 1 : 0;
         c.groups = c.fold ? 1 : 3;
@@ -1167,8 +1231,8 @@ anx_status anx_engine_set_conv(anx_engine *e, int32_t k, const float *weight, co
 
 size_t anx_engine_workspace_bytes(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w) {
     if (!e || !shape_ok(e, n, d, h, w)) return 0;
-    size_t total = 0;
-    for (auto &b : e->bufs) total += buffer_bytes(e, b, n, d, h, w);
+    std::vector<size_t> offs;
+    size_t total = plan_offsets(e, n, d, h, w, offs);
     for (auto &c : e->convs)
         if (c.inorm) total += align_up((size_t)n * c.ncols * 2 * sizeof(double), 256);
     return total;
@@ -1177,9 +1241,9 @@ size_t anx_engine_workspace_bytes(const anx_engine *e, int32_t n, int32_t d, int
 anx_status anx_engine_buffer_info(const anx_engine *e, int32_t n, int32_t d, int32_t h, int32_t w, int32_t index,
                                   size_t *offset, size_t *bytes, int32_t *level, int32_t *groups) {
     if (!e || !shape_ok(e, n, d, h, w) || index < 0 || index >= (int)e->bufs.size()) return ANX_ERR_BAD_ARG;
-    size_t off = 0;
-    for (int i = 0; i < index; ++i) off += buffer_bytes(e, e->bufs[i], n, d, h, w);
-    if (offset) *offset = off;
+    std::vector<size_t> offs;
+    plan_offsets(e, n, d, h, w, offs);
+    if (offset) *offset = offs[index];
     if (bytes) *bytes = buffer_bytes(e, e->bufs[index], n, d, h, w);
     if (level) *level = e->bufs[index].level;
     if (groups) *groups = e->bufs[index].groups;
@@ -1548,8 +1612,8 @@ anx_status anx_engine_step_stats(const anx_engine *e, int32_t step, int32_t n, i
     if (offset) *offset = 0;
     if (bytes) *bytes = 0;
     if ((s.kind != STEP_STEM && s.kind != STEP_CONV) || !e->convs[s.conv].inorm) return ANX_OK;
-    size_t off = 0;
-    for (auto &b : e->bufs) off += buffer_bytes(e, b, n, d, h, w);
+    std::vector<size_t> offs;
+    size_t off = plan_offsets(e, n, d, h, w, offs);
     for (int i = 0; i < s.conv; ++i)
         if (e->convs[i].inorm) off += align_up((size_t)n * e->convs[i].ncols * 2 * sizeof(double), 256);
     if (offset) *offset = off;

@@ -147,20 +147,30 @@ class Engine:
         wanted = sorted({i for i in layers if i in table and (not stop_early or i <= layers[-1])})
         last = table[layers[-1]][3] + 1 if stop_early else steps
         out = torch.empty((n, self.output_nc, d, h, w), dtype=torch.float32, device=self.device)
-        taps = []
+        taps = {}
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            self._check(self.lib.anx_engine_run_steps(
-                self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, 0, last))
-            for idx in wanted:
-                k, ch, lvl, _, is_output = table[idx]
+            # The workspace shares memory between tensors whose lifetimes do not overlap, so a tapped tensor is
+            # exported right after the launch that completes it, before later launches may reuse its region.
+            done = 0
+            for idx in sorted(wanted, key=lambda i: table[i][3]):
+                k, ch, lvl, last_step, is_output = table[idx]
+                upto = min(last_step + 1, last)
+                if upto > done:
+                    self._check(self.lib.anx_engine_run_steps(
+                        self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, done, upto))
+                    done = upto
                 if is_output:
-                    taps.append(out)
+                    taps[idx] = out
                     continue
                 t = torch.empty((n, ch, d >> lvl, h >> lvl, w >> lvl), dtype=torch.float32, device=self.device)
                 self._check(self.lib.anx_engine_export_tap(
                     self._h, k, n, d, h, w, ws.data_ptr(), ws.numel(), t.data_ptr(), stream))
-                taps.append(t)
+                taps[idx] = t
+            if last > done:
+                self._check(self.lib.anx_engine_run_steps(
+                    self._h, x.data_ptr(), out.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), stream, done, last))
+        taps = [taps[i] for i in wanted]
         return taps if stop_early else (out, taps)
 
     # -- forward ---------------------------------------------------------------

@@ -83,6 +83,9 @@ typedef struct anx_unet_desc {
 #define ANX_FLAG_NO_UPCONV 16u
 /* Run the thin 16 -> 16 layers on the generic tile kernel instead of the row kernel (tests compare the two). */
 #define ANX_FLAG_NO_ROWS 32u
+/* Give every intermediate tensor its own region of the workspace (no liveness-based sharing), so that all of them
+ * survive the forward: debugging / layer-by-layer comparisons.  Depth-slab engines never share regions. */
+#define ANX_FLAG_NO_WS_REUSE 64u
 
 /* Replaces: Unet.__init__ (network.py:262-465).  Builds the layer program and
  * device constants; no parameters yet. */
@@ -112,7 +115,10 @@ anx_status anx_engine_set_conv(anx_engine *engine, int32_t ordinal,
 
 /* Scratch the forward needs for a given input shape (activations between
  * layers; caller-owned so torch's caching allocator can serve it).  0 on a bad
- * shape.  Must be 256-byte aligned. */
+ * shape.  Must be 256-byte aligned.  Tensors whose lifetimes do not overlap share
+ * memory, so after a forward only the tensors still live at its end are intact:
+ * feature taps are exported right after the launch that completes them
+ * (anx_engine_tap_info: last_step). */
 size_t anx_engine_workspace_bytes(const anx_engine *engine, int32_t n, int32_t d,
                                   int32_t h, int32_t w);
 

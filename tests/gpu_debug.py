@@ -91,7 +91,7 @@ def main():
     state = O.random_state(cfg, seed=a.seed)
     shape = tuple(int(s) for s in a.shape.split(","))
     x = torch.rand(*shape, generator=torch.Generator().manual_seed(3))
-    eng = Engine(cfg, "cuda:0", flags=_lib.FLAG_FORCE_SIMT if a.simt else 0)
+    eng = Engine(cfg, "cuda:0", flags=(_lib.FLAG_FORCE_SIMT if a.simt else 0) | _lib.FLAG_NO_WS_REUSE | _lib.FLAG_NO_UPCONV)
     eng.load_state(state)
     y = eng.forward(x.cuda())
     torch.cuda.synchronize()

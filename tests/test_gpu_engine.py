@@ -1,13 +1,14 @@
 """Parity of the CUDA engine (through the C ABI) against the CPU oracle and the
 golden vectors minted from the reference.  Everything here needs a B200.
 
-Tolerances (floating point):
+Tolerances (floating point); measured values of round 2 on B200 in brackets
+(gpurun_out/parity_values.txt of the round, summarised in profiles/r2_summary.md):
   * LOOSE  engine (bf16 operands, fp32 accumulate) vs the fp32 oracle:
-           rel-L2 <= 3e-2 and per-voxel cosine >= 0.995.  For scale: the reference
-           itself under CPU bf16 autocast sits at rel-L2 1.8e-2 from its fp32 self.
+           rel-L2 <= 2e-2 and per-voxel cosine >= 0.998 [worst: 1.35e-2 / 0.99951; 7.9e-3 at 128^3].
+           For scale: the reference itself under CPU bf16 autocast sits at rel-L2 1.8e-2 from its fp32 self.
   * TIGHT  engine vs the oracle rounding to bf16 at the same points (weights after
-           BN folding, stored activations), fp32 accumulate: rel-L2 <= 1e-2.  The two
-           differ only by fp32 summation order, which flips an occasional bf16
+           BN folding, stored activations), fp32 accumulate: rel-L2 <= 8e-3 [worst: 6.2e-3; 3.7e-3 at
+           128^3].  The two differ only by fp32 summation order, which flips an occasional bf16
            rounding (measured: 3 of 16384 activations after the third conv, one ulp
            each); later layers spread such a flip, which is why this gate is not
            tighter.  The first two layers are additionally held to 1e-3.
@@ -31,7 +32,7 @@ from oracle import unet_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-LOOSE_REL, LOOSE_COS, TIGHT_REL = 3e-2, 0.995, 1e-2
+LOOSE_REL, LOOSE_COS, TIGHT_REL = 2e-2, 0.998, 8e-3
 
 
 def make_engine(cfg, state, flags=0):
@@ -112,7 +113,8 @@ def test_tensor_core_path_matches_simt_and_oracle_small(shape, cfgkw):
     state = O.random_state(cfg, seed=5)
     x = rand_input(shape, 9)
     ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
-    eng = make_engine(cfg, state, flags=_lib.FLAG_NO_UPCONV)     # same launch structure as the CUDA-core path
+    # same launch structure as the CUDA-core path; every intermediate tensor kept (compared layer by layer below)
+    eng = make_engine(cfg, state, flags=_lib.FLAG_NO_UPCONV | _lib.FLAG_NO_WS_REUSE)
     xs = x.cuda()
     y_ref = ref_eng.forward(xs)
     y = eng.forward(xs)
@@ -146,7 +148,7 @@ def test_instance_norm_path_small(shape, cfgkw):
     cfg = small_cfg(**cfgkw)
     state = O.random_state(cfg, seed=21)
     x = rand_input(shape, 13)
-    ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT)
+    ref_eng = make_engine(cfg, state, flags=_lib.FLAG_FORCE_SIMT | _lib.FLAG_NO_WS_REUSE)
     eng = make_engine(cfg, state)
     xs = x.cuda()
     y_ref = ref_eng.forward(xs)
@@ -179,7 +181,7 @@ def test_g4_dev_variant_94m_seeded_init():
     assert r <= LOOSE_REL and c >= LOOSE_COS, f"G4: rel-L2 {r:.3e}, min cosine {c:.5f}"
     emu = O.unet_forward(CFG_94M, sd, x, engine_rounding=True)
     # 24 re-normalised layers spread single rounding flips further than the 6M net does
-    assert rel_l2(y, emu) <= 2 * TIGHT_REL, f"G4 tight: {rel_l2(y, emu):.3e}"
+    assert rel_l2(y, emu) <= 2e-2, f"G4 tight: {rel_l2(y, emu):.3e}"
     m = m.cuda().eval()
     with torch.no_grad():
         assert m.engine_ineligible_reason(x.cuda()) is None
@@ -238,7 +240,7 @@ def test_g6_structured_inputs(state_6m):
         r = rel_l2(y[:, :, ::2, ::2, ::2], want)
         r_emu = rel_l2(emu[:, :, ::2, ::2, ::2], want)
         # correlated rounding on constant fields: one flipped ulp shifts a whole plateau
-        assert rel_l2(y, emu) <= 2.5 * TIGHT_REL, f"{name}: rel-L2 {rel_l2(y, emu):.3e} vs bf16-emulating oracle"
+        assert rel_l2(y, emu) <= 2.5e-2, f"{name}: rel-L2 {rel_l2(y, emu):.3e} vs bf16-emulating oracle"
         assert r <= max(LOOSE_REL, 1.2 * r_emu + 1e-3), f"{name}: rel-L2 {r:.3e} (bf16 emulation {r_emu:.3e})"
 
 
@@ -256,8 +258,8 @@ def test_full_batch_properties(state_6m):
     assert torch.equal(y1[0], y1[2]) and torch.equal(y1[0], y1[5]) and torch.equal(y1[1], y1[7])
     single = eng.forward(xs[1].cuda())
     assert torch.equal(single[0], y1[1]), "batched and single-volume results differ"
-    check_against_oracle(CFG_6M, state_6m, xs[0], y1[0:1], tight=False)
-    check_against_oracle(CFG_6M, state_6m, xs[1], y1[7:8], tight=False)
+    check_against_oracle(CFG_6M, state_6m, xs[0], y1[0:1], tight=True)
+    check_against_oracle(CFG_6M, state_6m, xs[1], y1[7:8], tight=True)
 
 
 def test_module_routes_to_engine_and_back(state_6m):
