@@ -44,6 +44,14 @@ constexpr int ROWS_STEM_THREADS = ROWS_THREADS + 128;
 constexpr int ROWS_STEM_TILE_BYTES = 2 * ROWS_X * 16;           // one input row: two K halves x 128 lanes x 16 B
 constexpr int ROWS_STEM_B_IMAGE_BYTES = 2 * ROWS_N * 16;        // one z rotation: all three dx taps live in K
 static_assert(ROWS_IN_Y * ROWS_STEM_TILE_BYTES <= ROWS_PLANE_BYTES, "a stem plane must fit a ring stage");
+// fp32 input staging of the stem: per plane ROWS_IN_Y row segments [x0 - 4, x0 + 132) (16-byte aligned on both
+// sides), bulk-copied by the producer warp several planes ahead of the builders.  The ring lives in the part of
+// the weight area the stem's small B images leave free.
+constexpr int ROWS_STEM_IN_ROW_BYTES = (ROWS_X + 8) * 4;
+constexpr int ROWS_STEM_IN_PLANE_BYTES = ROWS_IN_Y * ROWS_STEM_IN_ROW_BYTES;
+constexpr int ROWS_STEM_IN_STAGES = 5;
+static_assert(3 * ROWS_STEM_B_IMAGE_BYTES + ROWS_STEM_IN_STAGES * ROWS_STEM_IN_PLANE_BYTES <= 3 * ROWS_B_IMAGE_BYTES,
+              "stem input staging must fit behind the stem's B images");
 
 struct RowsGeom {
     int N, D, H, W;
@@ -59,6 +67,7 @@ struct RowsShared {
     uint64_t full_a[ROWS_STAGES], empty_a[ROWS_STAGES];
     uint64_t full_b;
     uint64_t acc_ready[2][2], drained[2][2];   // [strip][row pair]: hand-over at half-strip granularity
+    uint64_t full_in[ROWS_STEM_IN_STAGES], empty_in[ROWS_STEM_IN_STAGES];   // stem: fp32 input staging ring
     uint32_t tmem_slot;
     uint32_t pad[5];         // keeps `shift` 16-byte aligned (float4 reads of the head weights)
     float shift[16 + HEAD_FLOATS + 16];
@@ -89,6 +98,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
     if (threadIdx.x == 0) {
         for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], STEM ? 128 : 1); mbar_init(&sh->empty_a[i], 1); }
         mbar_init(&sh->full_b, 1);
+        for (int i = 0; i < ROWS_STEM_IN_STAGES; ++i) { mbar_init(&sh->full_in[i], 1); mbar_init(&sh->empty_in[i], 128); }
         for (int i = 0; i < 4; ++i) { mbar_init(&sh->acc_ready[i >> 1][i & 1], 1); mbar_init(&sh->drained[i >> 1][i & 1], 4); }
         fence_barrier_init();
     }
@@ -123,6 +133,32 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
             bulk_load_1d(b_img, wrows, B_BYTES, &sh->full_b);
         }
         uint32_t ka = 0;
+        if constexpr (STEM) {
+            // fp32 rows of input plane z0 - 1 + p (reflect at the global faces, or the attached neighbour planes):
+            // row i of the stage = input row reflect(y0 - 1 + i), floats [x0 - 4, x0 + 132) clipped to the volume
+            uint8_t *stage0 = b_img + 3 * ROWS_STEM_B_IMAGE_BYTES;
+            auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+            for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+                int n, x0, y0, z0;
+                decode(unit, n, x0, y0, z0);
+                const int gx_lo = x0 >= 4 ? x0 - 4 : 0, gx_hi = x0 + ROWS_X + 4 <= g.W ? x0 + ROWS_X + 4 : g.W;
+                const uint32_t bytes = (uint32_t)(gx_hi - gx_lo) * 4u, dst_off = (uint32_t)(gx_lo - (x0 - 4)) * 4u;
+                for (int p = 0; p < planes; ++p, ++ka) {
+                    const uint32_t k = ka % ROWS_STEM_IN_STAGES;
+                    if (lane == 0) {
+                        mbar_wait(&sh->empty_in[k], ((ka / ROWS_STEM_IN_STAGES) & 1) ^ 1, 27);
+                        mbar_arrive_expect_tx(&sh->full_in[k], ROWS_IN_Y * bytes);
+                    }
+                    __syncwarp();
+                    if (lane < ROWS_IN_Y) {
+                        const int zi = g.z_halo ? z0 + p : refl(z0 - 1 + p, g.D);
+                        const float *row = stem_in + (((size_t)n * (g.D + 2 * g.z_halo) + zi) * g.H + refl(y0 - 1 + lane, g.H)) * (size_t)g.W + gx_lo;
+                        bulk_load_1d(stage0 + (size_t)k * ROWS_STEM_IN_PLANE_BYTES + (size_t)lane * ROWS_STEM_IN_ROW_BYTES + dst_off,
+                                     row, bytes, &sh->full_in[k]);
+                    }
+                }
+            }
+        }
         if constexpr (!STEM)
         for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
             int n, x0, y0, z0;
@@ -148,27 +184,29 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
     } else if (STEM && warp >= 10) {
         // ------------------------------------------------- stem: A-tile builders
         const int bx = threadIdx.x - ROWS_THREADS;            // x voxel of the 128-wide tile
-        const int Dd = g.D, Hh = g.H, Ww = g.W;
-        auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+        const int Ww = g.W;
+        const uint8_t *stage0 = b_img + 3 * ROWS_STEM_B_IMAGE_BYTES;
         uint32_t ka = 0;
         for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
             int n, x0, y0, z0;
             decode(unit, n, x0, y0, z0);
             const int x = x0 + bx;
-            const int xm = refl(x - 1, Ww), xp = refl(x + 1, Ww);
+            // staged floats start at x0 - 4: x sits at bx + 4; reflect padding at the volume's x faces
+            const int im = x == 0 ? bx + 5 : bx + 3, ip = x == Ww - 1 ? bx + 3 : bx + 5;
             for (int p = 0; p < planes; ++p, ++ka) {
                 const uint32_t st = ka % ROWS_STAGES;
-                // input plane z0 - 1 + p: reflect at the global faces, or the attached neighbour planes (z_halo)
-                const int zi = g.z_halo ? z0 + p : refl(z0 - 1 + p, Dd);
-                const float *pl = stem_in + ((size_t)n * (Dd + 2 * g.z_halo) + zi) * ((size_t)Hh * Ww);
+                const uint32_t k = ka % ROWS_STEM_IN_STAGES;
+                mbar_wait(&sh->full_in[k], (ka / ROWS_STEM_IN_STAGES) & 1, 28);
+                const float *stg = reinterpret_cast<const float *>(stage0 + (size_t)k * ROWS_STEM_IN_PLANE_BYTES);
                 float v[ROWS_IN_Y][3];
 #pragma unroll
-                for (int i = 0; i < ROWS_IN_Y; ++i) {           // all loads of the plane in flight before the slot wait
-                    const float *row = pl + (size_t)refl(y0 - 1 + i, Hh) * Ww;
-                    v[i][0] = __ldg(row + xm);
-                    v[i][1] = __ldg(row + x);
-                    v[i][2] = __ldg(row + xp);
+                for (int i = 0; i < ROWS_IN_Y; ++i) {
+                    const float *row = stg + i * (ROWS_STEM_IN_ROW_BYTES / 4);
+                    v[i][0] = row[im];
+                    v[i][1] = row[bx + 4];
+                    v[i][2] = row[ip];
                 }
+                mbar_arrive(&sh->empty_in[k]);                // values are in registers: the producer may refill the stage
                 mbar_wait(&sh->empty_a[st], ((ka / ROWS_STAGES) & 1) ^ 1, 26);
                 uint8_t *tile = a_ring + (size_t)st * ROWS_PLANE_BYTES + (size_t)bx * 16;
 #pragma unroll

@@ -706,7 +706,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         Epilogue ep = make_epilogue(e, p, c, out);
         const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
         if (!force_simt && e->use_rows && c.d_wstem_rows && !ep.stats && p.W % ROWS_X == 0 && p.H % ROWS_YB == 0 &&
-            p.D % 16 == 0 && !exp_env("ANX_NO_STEM_ROWS")) {
+            p.D % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !exp_env("ANX_NO_STEM_ROWS")) {
             // row-form stem: the 16 -> 16 row kernel's pipeline with builder warps in front of it
             RowsGeom rg{};
             rg.N = p.N; rg.D = p.D; rg.H = p.H; rg.W = p.W;
