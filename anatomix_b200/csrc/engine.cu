@@ -857,14 +857,18 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
     case STEP_UP: {
         ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, s.dst_group_offset);
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
-        if (e->desc.interp_kind == ANX_INTERP_NEAREST)
-            upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
+        if (e->desc.interp_kind == ANX_INTERP_NEAREST) {
+            if (dst.D >= 4 && dst.H >= 4 && dst.W >= 32 && src.D <= 65535 && (size_t)p.N * s.groups <= 65535)
+                upsample2_nearest_grid_kernel<<<dim3(src.H, src.D, p.N * s.groups), std::min(128, dst.W), 0, st>>>(src, dst, s.groups);
+            else
+                upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
+        }
         else if (dst.D >= 4 && dst.H >= 4 && dst.W >= 32 && dst.D <= 65535 && (size_t)p.N * s.groups <= 65535) {
             const dim3 grid(dst.H, dst.D, p.N * s.groups);
             if (e->dt == DT_BF16)
-                upsample2_tri_grid_kernel<DT_BF16><<<grid, 128, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+                upsample2_tri_grid_kernel<DT_BF16><<<grid, std::min(128, dst.W), 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
             else
-                upsample2_tri_grid_kernel<DT_FP16><<<grid, 128, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+                upsample2_tri_grid_kernel<DT_FP16><<<grid, std::min(128, dst.W), 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
         }
         else
             upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(

@@ -208,6 +208,36 @@ upsample2_nearest_kernel(ActView src, ActView dst, int N, int groups) {
     }
 }
 
+// Nearest x2, grid-mapped: blockIdx = (low y, low z, n * groups + g), threads along the HIGH-resolution x.  Each thread
+// reads its low-resolution voxel once and writes the 2 x 2 (z, y) copies: every warp store is a contiguous 512-byte
+// run; strides and the y / z mirror offsets are per block, no per-voxel index decomposition.
+__global__ void __launch_bounds__(128)
+upsample2_nearest_grid_kernel(ActView src, ActView dst, int groups) {
+    const int yl = blockIdx.x, zl = blockIdx.y;
+    const int n = blockIdx.z / groups, gidx = blockIdx.z - n * groups;
+    const uint4 *srow = src.at(n, gidx, zl + 1, yl + 1, 1);
+    const size_t drow = (size_t)dst.pitch, dplane = drow * (dst.H + 2);
+    uint4 *d00 = dst.at(n, gidx, 2 * zl + 1, 2 * yl + 1, 1);
+    int mdy[2], mdz[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        mdy[a] = mirror_delta(2 * yl + a, dst.H, dst.shell_rep);
+        mdz[a] = mirror_delta_z(2 * zl + a, dst.D, dst.shell_rep, dst.z_open);
+    }
+    for (int x = threadIdx.x; x < dst.W; x += blockDim.x) {
+        const uint4 q = __ldg(srow + (x >> 1));
+        const int mdx = mirror_delta(x, dst.W, dst.shell_rep);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                uint4 *pd = d00 + (size_t)a * dplane + (size_t)b * drow + x;
+                *pd = q;
+                if (mdx | mdy[b] | mdz[a]) store_mirrors(pd, q, mdz[a], mdy[b], mdx, drow, dplane);
+            }
+    }
+}
+
 // z axis of a depth slab (one oversized volume split over several GPUs): at an interior slab face the
 // interpolation reads the neighbour's boundary plane from the shell (index -1 / n) instead of clamping.
 __device__ __forceinline__ void tri_src_slab(int o, int n, bool lo_open, bool hi_open, int &i0, int &i1, float &t) {
@@ -280,7 +310,7 @@ upsample2_tri_grid_kernel(ActView src, ActView dst, int groups, int z_lo_open, i
     uint4 *prow = dst.at(n, gidx, z + 1, y + 1, 1);
     const int mdy = mirror_delta(y, dst.H, dst.shell_rep), mdz = mirror_delta_z(z, dst.D, dst.shell_rep, dst.z_open);
     const float wz[2] = {1.0f - tz, tz}, wy[2] = {1.0f - ty, ty};
-    for (int x = threadIdx.x; x < dst.W; x += 128) {
+    for (int x = threadIdx.x; x < dst.W; x += blockDim.x) {
         int x0, x1;
         float tx;
         tri_src(x, src.W, x0, x1, tx);

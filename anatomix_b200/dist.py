@@ -144,6 +144,9 @@ class FeatureGather:
         dev = self.engine.device
         main = torch.cuda.current_stream(dev)
         mine = buf[self.rank * n:(self.rank + 1) * n]
+        if self._done[b] is not None:
+            # the copy engines may still be reading this slot's previous content (push of `depth` submissions ago)
+            main.wait_event(self._done[b])
         if self.mode == "fused":
             hdl.barrier()                               # every rank is done reading this buffer's previous content
             self.engine.forward_gather(shard, list(hdl.buffer_ptrs), self.rank,

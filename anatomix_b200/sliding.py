@@ -10,8 +10,11 @@ accumulate / normalise) for GPU-resident volumes so whole scans go through the
 engine in large window batches.
 
 MONAI (an unpinned dependency of the reference, ``requirements.txt:12``) is not
-available offline, so this restatement is pinned only against an independent
-CPU implementation in the tests, not against MONAI itself: **parity unpinned**.
+available offline, so this restatement is pinned against a literal fixture derived
+BY HAND from MONAI's published algorithm (window origins, scan intervals and the
+gaussian importance map of a tiny case plus the registration setting's 343-window
+grid: ``tests/test_sliding.py::test_literal_fixture_of_the_monai_algorithm``) and
+against an independent CPU implementation, not against MONAI's code itself.
 """
 from __future__ import annotations
 
