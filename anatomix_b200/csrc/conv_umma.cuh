@@ -112,12 +112,15 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             uint32_t ka = 0, kb = 0;
-            if (g.b_static && blockIdx.x < g.total_tiles) {   // the one weight slab of this layer: resident for the whole launch
+            if (g.b_static && blockIdx.x < g.total_tiles) {   // the weights of this layer: resident for the whole launch
                 if (ANX_ABL(g, 8)) {
                     mbar_arrive(&sh->full_b[0]);
                 } else {
                     mbar_arrive_expect_tx(&sh->full_b[0], g.b_stage_bytes);
-                    bulk_load_1d(b_ring, wpack, g.b_stage_bytes, &sh->full_b[0]);
+                    for (uint32_t off = 0; off < g.b_stage_bytes; off += 32768u) {      // bulk copies of at most 32 KB
+                        const uint32_t len = g.b_stage_bytes - off < 32768u ? g.b_stage_bytes - off : 32768u;
+                        bulk_load_1d(b_ring + off, wpack + off, len, &sh->full_b[0]);
+                    }
                 }
             }
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -210,6 +213,17 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
                         for (int b = 0; b < g.bz; ++b) {
                             const uint32_t dcol = acc + b * g.ncols;
                             const uint32_t aj = a_lo + (b + grp) * (HALO_Y * HALO_X);   // grp = kz = dz + 1
+                            if (g.trim == 2) { // ... and the compact tiles of every tap resident in shared memory
+                                const uint32_t b_base = (smem_u32(b_ring) & 0x3FFFF) >> 4;
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) {
+                                    const uint32_t lo = 16u * g.trim_lo[grp * 9 + t], nn = 16u * g.trim_n[grp * 9 + t];
+                                    const uint32_t bt = b_base + g.trim_off[(c * 3 + grp) * 9 + t];
+                                    umma_bf16_warp(dcol + lo, make_desc(a_hi, aj + (t / 3) * HALO_X + (t % 3)),
+                                                   make_desc(b_hi, bt | ((nn & 0x3FFF) << 16)), idesc_m128(nn, g.dt));
+                                }
+                                continue;
+                            }
                             if (g.trim) {      // structurally sparse B: only the columns this tap can reach
 #pragma unroll
                                 for (int t = 0; t < 9; ++t) {

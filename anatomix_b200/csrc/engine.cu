@@ -106,6 +106,8 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
     void *d_wrows = nullptr;  // 16 -> 16 row kernel: three B images [z rotation][dx][k half][144 rows][8] (conv_rows.cuh)
+    void *d_wtrim = nullptr;  // low-resolution decoder half: compact per-tap tiles of the non-zero column spans (resident B)
+    size_t wtrim_bytes = 0;
     void *d_wstem_rows = nullptr;   // row-form stem (Cin = 1, 16 columns): three bf16 B images [z rotation][k half][144 rows][8]
     float *d_bias = nullptr;  // [ncols]
     size_t wpack_bytes = 0;
@@ -483,6 +485,18 @@ size_t plan_offsets(const anx_engine *e, int n, int d, int h, int w, std::vector
     return total;
 }
 
+// Low-resolution half of a decoder conv: column (parity p = a*4 + b*2 + c, channel) of low-resolution tap offset o
+// in {-1, 0, +1} along an axis is non-zero only for parity 0 (o = -1), both (o = 0) or parity 1 (o = +1) of that
+// axis (see anx_engine_set_conv).  Span of 16-column blocks tap (kz, ky, kx) reaches; `blocks` = blocks per parity.
+void trim_span(int kz, int ky, int kx, int blocks, int &lo, int &n) {
+    auto span = [](int o, int &l, int &h) { l = o == 2 ? 1 : 0; h = o == 0 ? 0 : 1; };   // o = offset + 1
+    int al, ah, bl, bh, cl, ch;
+    span(kz, al, ah); span(ky, bl, bh); span(kx, cl, ch);
+    const int pmin = al * 4 + bl * 2 + cl, pmax = ah * 4 + bh * 2 + ch;
+    lo = pmin * blocks;
+    n = (pmax - pmin + 1) * blocks;
+}
+
 // Tile / pipeline configuration of one tensor-core conv at one shape.
 ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H, int W, int in_groups_total) {
     ConvGeom g{};
@@ -541,22 +555,35 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     if (const char *ab = exp_env("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
     g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
                               sizeof(UmmaShared));
-    // Low-resolution half of a decoder conv: column (parity p = a*4 + b*2 + c, channel) of low-resolution tap
-    // offset o in {-1, 0, +1} along an axis is non-zero only for parity 0 (o = -1), both (o = 0) or parity 1
-    // (o = +1) of that axis (see anx_engine_set_conv).  Each tap's MMA covers just the span of its parities.
+    // Low-resolution half of a decoder conv: each tap's MMA covers just the span of its parities (trim_span); when the
+    // compact tiles of the whole layer fit next to the A ring they stay resident in shared memory, loaded once per CTA
+    // instead of streaming 221 KB of (mostly zero) slabs from L2 for every tile.
     if (c.d2s_cout > 0 && !c.fold && c.n_splits == 1 && c.d2s_cout % 16 == 0 && !exp_env("ANX_NO_TRIM")) {
         g.trim = 1;
         const int blocks = c.d2s_cout / 16;        // 16-column blocks per parity
-        auto span = [](int o, int &lo, int &hi) { lo = o == 2 ? 1 : 0; hi = o == 0 ? 0 : 1; };   // o = offset + 1
-        for (int kz = 0; kz < 3; ++kz)
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx) {
-                    int al, ah, bl, bh, cl, ch;
-                    span(kz, al, ah); span(ky, bl, bh); span(kx, cl, ch);
-                    const int pmin = al * 4 + bl * 2 + cl, pmax = ah * 4 + bh * 2 + ch;
-                    g.trim_lo[kz * 9 + ky * 3 + kx] = (uint8_t)(pmin * blocks);
-                    g.trim_n[kz * 9 + ky * 3 + kx] = (uint8_t)((pmax - pmin + 1) * blocks);
+        uint32_t off16 = 0;
+        for (int t = 0; t < 27; ++t) {
+            int lo, n;
+            trim_span(t / 9, (t % 9) / 3, t % 3, blocks, lo, n);
+            g.trim_lo[t] = (uint8_t)lo;
+            g.trim_n[t] = (uint8_t)n;
+        }
+        if (c.d_wtrim && g.cin_chunks <= 4 && !exp_env("ANX_NO_BRESIDENT")) {
+            for (int ch = 0; ch < g.cin_chunks; ++ch)
+                for (int t = 0; t < 27; ++t) {
+                    g.trim_off[ch * 27 + t] = (uint16_t)off16;
+                    off16 += 2u * 16u * g.trim_n[t];             // two K halves x rows, one 16-byte unit per row
                 }
+            const size_t need = (size_t)g.a_stages * g.a_stage_bytes + (size_t)off16 * 16 + sizeof(UmmaShared);
+            if ((size_t)off16 * 16 == c.wtrim_bytes && need + 1024 <= (size_t)e->max_smem && off16 < 65536u) {
+                g.trim = 2;
+                g.b_static = 1;
+                g.b_stages = 1;
+                g.b_stage_bytes = (uint32_t)c.wtrim_bytes;
+                g.trim_bytes = (uint32_t)c.wtrim_bytes;
+                g.smem_bytes = (uint32_t)need;
+            }
+        }
     }
     return g;
 }
@@ -829,7 +856,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                 src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
         } else {
             const int grid = std::min(g.total_tiles, e->num_sms);
-            const uint8_t *wp_ = (const uint8_t *)c.d_wpack;
+            const uint8_t *wp_ = (const uint8_t *)(g.trim == 2 ? c.d_wtrim : c.d_wpack);
 #define ANX_CONV(MODE_) conv3_umma_kernel<MODE_><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g, wp_, ep)
             if (ep.mode == OUT_NCDHW_F32) {
                 if (ep.cl16) ANX_CONV(EPI_CL16);
@@ -1019,6 +1046,7 @@ void anx_engine_destroy(anx_engine *e) {
         if (c.d_wpack) cudaFree(c.d_wpack);
         if (c.d_wstem) cudaFree(c.d_wstem);
         if (c.d_wstem_rows) cudaFree(c.d_wstem_rows);
+        if (c.d_wtrim) cudaFree(c.d_wtrim);
         if (c.d_wrows) cudaFree(c.d_wrows);
         if (c.d_bias) cudaFree(c.d_bias);
     }
@@ -1152,6 +1180,29 @@ static anx_status upload_conv(anx_engine *e, ConvLayer &c, const std::vector<flo
             ANX_CUDA(e, cudaMalloc(&c.d_wrows, img.size() * 2));
             ANX_CUDA(e, cudaMemcpy(c.d_wrows, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
         }
+    }
+    if (c.d_wtrim) { cudaFree(c.d_wtrim); c.d_wtrim = nullptr; c.wtrim_bytes = 0; }
+    if (!c.is_stem && c.d2s_cout > 0 && !c.fold && c.n_splits == 1 && c.d2s_cout % 16 == 0) {
+        // compact tiles [chunk][kz][tap(ky,kx)] -> [k half][rows of the tap's column span][8] (make_geom: trim == 2)
+        const int chunks = c.cin / 16, blocks = c.d2s_cout / 16;
+        std::vector<uint16_t> img;
+        for (int ch = 0; ch < chunks; ++ch)
+            for (int t = 0; t < 27; ++t) {
+                int lo, n;
+                trim_span(t / 9, (t % 9) / 3, t % 3, blocks, lo, n);
+                const size_t at = img.size();
+                img.resize(at + (size_t)2 * 16 * n * 8, 0);
+                for (int kc = 0; kc < 2; ++kc)
+                    for (int r = 0; r < 16 * n; ++r)
+                        for (int el = 0; el < 8; ++el) {
+                            const int o = 16 * lo + r, i = ch * 16 + kc * 8 + el;
+                            const float v = o < c.cout ? w[((size_t)o * c.cin + i) * 27 + t] : 0.0f;
+                            img[at + ((size_t)kc * 16 * n + r) * 8 + el] = e->dt == DT_BF16 ? f32_to_bf16_rne(v) : f32_to_f16_rne(v);
+                        }
+            }
+        c.wtrim_bytes = img.size() * 2;
+        ANX_CUDA(e, cudaMalloc(&c.d_wtrim, c.wtrim_bytes));
+        ANX_CUDA(e, cudaMemcpy(c.d_wtrim, img.data(), c.wtrim_bytes, cudaMemcpyHostToDevice));
     }
     ANX_CUDA(e, cudaMalloc(&c.d_bias, c.ncols * sizeof(float)));
     ANX_CUDA(e, cudaMemcpy(c.d_bias, shift.data(), c.ncols * sizeof(float), cudaMemcpyHostToDevice));

@@ -158,6 +158,10 @@ struct ConvGeom {
     // on that column range.  trim = 0: every tap covers all ncols columns.
     int trim;
     uint8_t trim_lo[27], trim_n[27];   // in units of 16 columns
+    // trim == 2: the trimmed weights of the WHOLE layer are resident in shared memory (loaded once per CTA): tap
+    // (chunk, dz group, dy*3+dx) is a compact K-major tile of trim_n rows at trim_off (16-byte units) from the image.
+    uint16_t trim_off[4 * 27];
+    uint32_t trim_bytes;
 };
 
 }   // namespace anx
