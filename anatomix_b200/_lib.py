@@ -43,6 +43,7 @@ EXPORTS = [
     "anx_engine_forward_gather", "anx_engine_forward_cl16", "anx_engine_storage_type", "anx_widen_cl16_f32",
     "anx_push_to_peers", "anx_engine_forward_slab", "anx_engine_forward_host_ex",
     "anx_engine_forward_concat", "anx_channel_normalize_f32",
+    "anx_engine_tap_kind", "anx_engine_set_tap_conv", "anx_engine_export_prenorm_tap",
 ]
 
 
@@ -132,6 +133,12 @@ def load():
     lib.anx_engine_forward_concat.restype = i32
     lib.anx_channel_normalize_f32.argtypes = [vp, vp, C.c_int64, i32, i32, i32, i32, i32, C.c_float, vp]
     lib.anx_channel_normalize_f32.restype = i32
+    lib.anx_engine_tap_kind.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.anx_engine_tap_kind.restype = i32
+    lib.anx_engine_set_tap_conv.argtypes = [vp, i32, vp, vp, i32]
+    lib.anx_engine_set_tap_conv.restype = i32
+    lib.anx_engine_export_prenorm_tap.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, sz, vp, vp]
+    lib.anx_engine_export_prenorm_tap.restype = i32
     lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_row_layout.restype = i32
     lib.anx_engine_set_head.argtypes = [vp, i32, vp, vp, i32]

@@ -93,6 +93,7 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     int cin, cout, ncols;     // ncols = cout rounded up to 16
     int level;                // resolution level
     bool has_norm, has_act, is_stem, is_final;
+    bool is_tap = false;      // un-folded clone of a conv that writes its PRE-norm output as fp32 NCDHW (feature taps)
     int src_buf, dst_buf, dst_group_offset;   // buffer ids (-1: network input / output)
     // device parameters
     bool ready = false;
@@ -144,6 +145,8 @@ struct TapSite {
     int buffer, group_offset, groups;   // buffer -1: the network output
     int channels, level;
     int last_step;                      // the tensor is complete once steps [0, last_step] have run
+    int prenorm_conv = -1;              // >= 0: PRE-norm output of logical conv `prenorm_conv` (buffer = -2): not stored,
+                                        // re-evaluated on request by an un-folded clone of that conv right after last_step
 };
 
 struct GatherArgs {           // where and how the final conv stores (one forward call)
@@ -177,6 +180,7 @@ struct anx_engine {
     std::vector<Buffer> bufs;
     std::vector<Step> steps;
     std::vector<TapSite> taps;
+    std::vector<ConvLayer> tap_convs;   // per logical conv: un-folded clone for pre-norm taps (ready once anx_engine_set_tap_conv ran)
     // optional linear head fused into the last conv's epilogue (anx_engine_set_head)
     // depth-slab mode (anx_engine_set_slab): which z faces of this slab have a neighbour, and the depth of the
     // whole volume (instance-norm statistics are per whole volume)
@@ -391,6 +395,17 @@ void build_taps(anx_engine *e) {
                 e->taps.push_back(TapSite{c.module_index, -1, 0, (c.cout + 7) / 8, c.cout, 0, last});
                 continue;
             }
+            // The conv slot itself, when a norm follows: the reference taps the conv's output BEFORE the norm
+            // (network.py:504-515; the pretraining defaults tap these slots).  The engine never stores that tensor
+            // (BatchNorm is folded into the weights, InstanceNorm overwrites it in place): an un-folded clone of the
+            // conv re-evaluates it on request.  Not for a conv that runs as two launches (see build_program).
+            if (c.has_norm)
+                for (int k = 0; k < (int)e->logical.size(); ++k)
+                    if (e->logical[k].conv_a == s.conv && e->logical[k].conv_b < 0) {
+                        TapSite t{c.module_index, -2, 0, c.cout / 8, c.cout, c.level, si};
+                        t.prenorm_conv = k;
+                        e->taps.push_back(t);
+                    }
             // the stored tensor is the conv's output after norm and activation: the tap of the LAST slot of
             // the conv block (act if present, else norm, else the conv itself)
             const int idx = c.module_index + (c.has_norm ? 1 : 0) + (c.has_act ? 1 : 0);
@@ -676,7 +691,7 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
     }
     ep.head_nc = 0;
     ep.head = nullptr;
-    if (c.is_final && e->head_nc > 0) {
+    if (c.is_final && !c.is_tap && e->head_nc > 0) {
         ep.head_nc = e->head_nc;
         ep.head = e->d_head;
     }
@@ -687,8 +702,9 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         ep.cl16 = ga->payload == ANX_PAYLOAD_CL16 ? 1 : 0;
     }
     if (c.is_final) {
-        const size_t chans = e->head_nc > 0 ? (size_t)e->head_nc : (size_t)c.cout;
-        ep.out_nstride = (ga && ga->out_nstride) ? ga->out_nstride : chans * (size_t)p.D * p.H * p.W;
+        const size_t chans = (e->head_nc > 0 && !c.is_tap) ? (size_t)e->head_nc : (size_t)c.cout;
+        ep.out_nstride = (ga && ga->out_nstride) ? ga->out_nstride
+                                                 : chans * (size_t)(p.D >> c.level) * (p.H >> c.level) * (p.W >> c.level);
     }
     ep.cout = c.cout;
     ep.bias = c.d_bias;
@@ -708,8 +724,8 @@ Epilogue make_epilogue(const anx_engine *e, const ShapePlan &p, const ConvLayer 
         ep.dst.base = nullptr;
         ep.dst.groups_total = 0;
         ep.dst.group_offset = 0;
-        ep.dst.D = p.D; ep.dst.H = p.H; ep.dst.W = p.W;
-        ep.dst.lead = 0; ep.dst.pitch = p.W;
+        ep.dst.D = p.D >> c.level; ep.dst.H = p.H >> c.level; ep.dst.W = p.W >> c.level;   // level 0 except for tap clones
+        ep.dst.lead = 0; ep.dst.pitch = p.W >> c.level;
     } else {
         ep.mode = OUT_PADDED_BF16;
         ep.dst = view_of(e, p, c.dst_buf, c.dst_group_offset);
@@ -725,11 +741,12 @@ int grid_for(size_t work_items, int threads, int num_sms, int waves) {
 }
 
 anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const float *in, float *out,
-                       cudaStream_t st, const GatherArgs *ga = nullptr) {
+                       cudaStream_t st, const GatherArgs *ga = nullptr, const ConvLayer *conv_override = nullptr,
+                       const ConvGeom *geom_override = nullptr) {
     const bool force_simt = (e->desc.flags & ANX_FLAG_FORCE_SIMT) != 0;
     switch (s.kind) {
     case STEP_STEM: {
-        const ConvLayer &c = e->convs[s.conv];
+        const ConvLayer &c = conv_override ? *conv_override : e->convs[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out);
         const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
         if (!force_simt && e->use_rows && c.d_wstem_rows && !ep.stats && p.W % ROWS_X == 0 && p.H % ROWS_YB == 0 &&
@@ -746,8 +763,12 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             if (const char *ab = exp_env("ANX_ABLATE")) rg.ablate = (uint32_t)atoi(ab);
             rg.smem_bytes = (uint32_t)(ROWS_STAGES * ROWS_PLANE_BYTES + 3 * ROWS_B_IMAGE_BYTES + sizeof(RowsShared));
             const int grid = std::min(rg.total_units, e->num_sms);
-            conv3_rows_kernel<EPI_PADDED, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
-                ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
+            if (ep.mode == OUT_NCDHW_F32)      // pre-norm tap of the stem
+                conv3_rows_kernel<EPI_F32, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
+                    ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
+            else
+                conv3_rows_kernel<EPI_PADDED, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
+                    ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
             break;
         }
         if (!force_simt && c.d_wstem && p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
@@ -792,7 +813,9 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const int grid = std::min(g.total_tiles, e->num_sms);
             const uint8_t *ws_ = (const uint8_t *)c.d_wstem;
 #define ANX_STEM(KQ_, MODE_) stem_umma_kernel<KQ_, MODE_><<<grid, STEM_THREADS, g.smem_bytes, st>>>(tm, g, ws_, ep)
-            if (ep.stats) {
+            if (ep.mode == OUT_NCDHW_F32) {   // pre-norm tap of the stem
+                if (g.kq == 1) ANX_STEM(1, EPI_F32); else if (g.kq == 2) ANX_STEM(2, EPI_F32); else ANX_STEM(3, EPI_F32);
+            } else if (ep.stats) {
                 if (g.kq == 1) ANX_STEM(1, EPI_STATS); else if (g.kq == 2) ANX_STEM(2, EPI_STATS); else ANX_STEM(3, EPI_STATS);
             } else {
                 if (g.kq == 1) ANX_STEM(1, EPI_PADDED); else if (g.kq == 2) ANX_STEM(2, EPI_PADDED); else ANX_STEM(3, EPI_PADDED);
@@ -815,8 +838,8 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         break;
     }
     case STEP_CONV: {
-        const ConvLayer &c = e->convs[s.conv];
-        const ConvGeom &g = p.geoms[s.conv];
+        const ConvLayer &c = conv_override ? *conv_override : e->convs[s.conv];
+        const ConvGeom &g = geom_override ? *geom_override : p.geoms[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out, ga, force_simt ? nullptr : &g);
         if (ep.head_nc > 0 && (force_simt || ep.n_peers > 0 || ep.cl16))
             return e->fail(ANX_ERR_UNSUPPORTED, "a fused output head needs the tensor-core path with the plain fp32 output");
@@ -1014,6 +1037,8 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     ANX_SMEM(conv3_rows_kernel<EPI_SEEDED>); ANX_SMEM(conv3_rows_kernel<EPI_POOL>);
     ANX_SMEM((stem_umma_kernel<1, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<2, EPI_PADDED>)); ANX_SMEM((stem_umma_kernel<3, EPI_PADDED>));
     ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
+    ANX_SMEM((stem_umma_kernel<1, EPI_F32>)); ANX_SMEM((stem_umma_kernel<2, EPI_F32>)); ANX_SMEM((stem_umma_kernel<3, EPI_F32>));
+    ANX_SMEM((conv3_rows_kernel<EPI_F32, true>));
 #undef ANX_SMEM
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -1041,6 +1066,14 @@ void anx_engine_destroy(anx_engine *e) {
     for (int i = 0; i < 8; ++i) {
         if (e->push_stream[i]) cudaStreamDestroy(e->push_stream[i]);
         if (e->ev_push_done[i]) cudaEventDestroy(e->ev_push_done[i]);
+    }
+    for (auto &c : e->tap_convs) {
+        if (c.d_wpack) cudaFree(c.d_wpack);
+        if (c.d_wstem) cudaFree(c.d_wstem);
+        if (c.d_wstem_rows) cudaFree(c.d_wstem_rows);
+        if (c.d_wtrim) cudaFree(c.d_wtrim);
+        if (c.d_wrows) cudaFree(c.d_wrows);
+        if (c.d_bias) cudaFree(c.d_bias);
     }
     for (auto &c : e->convs) {
         if (c.d_wpack) cudaFree(c.d_wpack);
@@ -1718,7 +1751,7 @@ anx_status anx_engine_tap_info(const anx_engine *e, int32_t k, int32_t *module_i
     if (channels) *channels = t.channels;
     if (level) *level = t.level;
     if (last_step) *last_step = t.last_step;
-    if (is_output) *is_output = t.buffer < 0 ? 1 : 0;
+    if (is_output) *is_output = t.buffer == -1 ? 1 : 0;
     return ANX_OK;
 }
 
@@ -1727,7 +1760,7 @@ anx_status anx_engine_export_tap(anx_engine *e, int32_t k, int32_t n, int32_t d,
     if (!e) return ANX_ERR_BAD_ARG;
     if (k < 0 || k >= (int)e->taps.size() || !out) return e->fail(ANX_ERR_BAD_ARG, "bad tap ordinal or null output");
     const TapSite &t = e->taps[k];
-    if (t.buffer < 0) return e->fail(ANX_ERR_BAD_ARG, "tap %d is the network output: it is already fp32 NCDHW", k);
+    if (t.buffer < 0) return e->fail(ANX_ERR_BAD_ARG, "tap %d is not a stored tensor (network output or pre-norm tap)", k);
     if (!shape_ok(e, n, d, h, w)) return e->fail(ANX_ERR_BAD_SHAPE, "bad shape for a tap export");
     const size_t need = anx_engine_workspace_bytes(e, n, d, h, w);
     if (!workspace || ws_bytes < need) return e->fail(ANX_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", ws_bytes, need);
@@ -1741,6 +1774,61 @@ anx_status anx_engine_export_tap(anx_engine *e, int32_t k, int32_t n, int32_t d,
         src, n, t.groups, t.channels, out, e->dt);
     ANX_CUDA(e, cudaGetLastError());
     return ANX_OK;
+}
+
+anx_status anx_engine_tap_kind(const anx_engine *e, int32_t k, int32_t *kind, int32_t *conv_ordinal) {
+    if (!e || k < 0 || k >= (int)e->taps.size()) return ANX_ERR_BAD_ARG;
+    const TapSite &t = e->taps[k];
+    if (kind) *kind = t.prenorm_conv >= 0 ? ANX_TAP_PRENORM : (t.buffer < 0 ? ANX_TAP_OUTPUT : ANX_TAP_STORED);
+    if (conv_ordinal) *conv_ordinal = t.prenorm_conv;
+    return ANX_OK;
+}
+
+anx_status anx_engine_set_tap_conv(anx_engine *e, int32_t k, const float *weight, const float *bias, int32_t location) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (k < 0 || k >= (int)e->logical.size() || !weight) return e->fail(ANX_ERR_BAD_ARG, "bad conv ordinal or null weight");
+    const Logical &L = e->logical[k];
+    if (L.conv_b >= 0 || !L.has_norm)
+        return e->fail(ANX_ERR_UNSUPPORTED, "conv %d has no pre-norm tap on this engine", L.module_index);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    if (e->tap_convs.size() != e->logical.size()) e->tap_convs.resize(e->logical.size());
+    ConvLayer &t = e->tap_convs[k];
+    const ConvLayer &src = e->convs[L.conv_a];
+    void *keep[6] = {t.d_wpack, t.d_wstem, t.d_wrows, t.d_wtrim, t.d_wstem_rows, t.d_bias};   // upload_conv frees / replaces these
+    t = src;
+    t.d_wpack = keep[0]; t.d_wstem = keep[1]; t.d_wrows = keep[2]; t.d_wtrim = keep[3]; t.d_wstem_rows = keep[4];
+    t.d_bias = static_cast<float *>(keep[5]);
+    t.is_tap = true; t.is_final = true; t.has_norm = false; t.has_act = false; t.inorm = false;
+    t.pool_dst_buf = -1; t.seed_buf = -1; t.d2s_cout = 0; t.dst_buf = -1; t.ready = false;
+    const size_t nw = (size_t)L.cout * L.cin * 27;
+    std::vector<float> hw(nw), shift(t.ncols, 0.0f);
+    const cudaMemcpyKind kind = location == ANX_LOC_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    ANX_CUDA(e, cudaMemcpy(hw.data(), weight, nw * sizeof(float), kind));
+    if (bias) ANX_CUDA(e, cudaMemcpy(shift.data(), bias, L.cout * sizeof(float), kind));
+    return upload_conv(e, t, hw, shift);      // no fold: the clone computes conv(x) + bias
+}
+
+anx_status anx_engine_export_prenorm_tap(anx_engine *e, int32_t tap, const float *in, int32_t n, int32_t d, int32_t h,
+                                         int32_t w, void *workspace, size_t ws_bytes, float *out, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    if (tap < 0 || tap >= (int)e->taps.size() || e->taps[tap].prenorm_conv < 0 || !out || !in)
+        return e->fail(ANX_ERR_BAD_ARG, "tap %d is not a pre-norm tap (or null pointers)", tap);
+    const TapSite &t = e->taps[tap];
+    if ((int)e->tap_convs.size() <= t.prenorm_conv || !e->tap_convs[t.prenorm_conv].ready)
+        return e->fail(ANX_ERR_NOT_READY, "anx_engine_set_tap_conv has not been called for conv ordinal %d", t.prenorm_conv);
+    if (!shape_ok(e, n, d, h, w)) return e->fail(ANX_ERR_BAD_SHAPE, "bad shape for a tap export");
+    const size_t need = anx_engine_workspace_bytes(e, n, d, h, w);
+    if (!workspace || ws_bytes < need) return e->fail(ANX_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", ws_bytes, need);
+    ANX_CUDA(e, cudaSetDevice(e->desc.device));
+    std::shared_ptr<ShapePlan> p;
+    anx_status st = get_plan(e, n, d, h, w, workspace, p);
+    if (st != ANX_OK) return st;
+    // Re-run the conv's launch (its input tensor is still live: this is called right after step `last_step`) with
+    // the un-folded clone and the fp32 NCDHW epilogue; tiles / tensor map are those of the original launch.
+    const Step &s = e->steps[t.last_step];
+    ConvGeom g = p->geoms[s.conv];
+    g.fuse_pool = 0;
+    return launch_step(e, *p, s, in, out, static_cast<cudaStream_t>(stream), nullptr, &e->tap_convs[t.prenorm_conv], &g);
 }
 
 anx_status anx_avgpool3d_scale_f32(const float *in, float *out, int64_t nc, int32_t d, int32_t h, int32_t w,

@@ -59,6 +59,7 @@ class Engine:
         self.input_nc = cfg["input_nc"]
         self.flags = flags
         self._workspaces: Dict[tuple, torch.Tensor] = {}
+        self._state, self._tap_convs_ready = None, set()
 
     # -- lifetime ----------------------------------------------------------
     def close(self):
@@ -89,6 +90,8 @@ class Engine:
     def load_state(self, state: dict):
         """Feeds a reference-format state dict (``model.<idx>.weight`` ...)."""
         norm = self.cfg.get("norm", "batch")
+        self._state = state            # pre-norm tap clones are packed from it on first use (`_ensure_tap_conv`)
+        self._tap_convs_ready = set()
         for k, (idx, cin, cout, has_norm) in enumerate(self.conv_table()):
             def host(name):
                 t = torch.as_tensor(state[name]).detach().to("cpu", torch.float32).contiguous()
@@ -125,14 +128,31 @@ class Engine:
 
     # -- feature taps ------------------------------------------------------------
     def tap_table(self):
-        """{module_index: (ordinal, channels, level, last_step, is_output)} of the tensors the engine
-        can hand out for ``forward(layers=[...])`` (anx_engine_tap_info)."""
+        """{module_index: (ordinal, channels, level, last_step, is_output, prenorm_conv)} of the tensors the
+        engine can hand out for ``forward(layers=[...])`` (anx_engine_tap_info / anx_engine_tap_kind).
+        ``prenorm_conv`` >= 0: the PRE-norm output of that conv ordinal, re-evaluated by an un-folded clone."""
         out = {}
         for k in range(self.lib.anx_engine_num_taps(self._h)):
             v = [C.c_int32() for _ in range(5)]
             self._check(self.lib.anx_engine_tap_info(self._h, k, *[C.byref(x) for x in v]))
-            out[v[0].value] = (k, v[1].value, v[2].value, v[3].value, bool(v[4].value))
+            kind, conv = C.c_int32(), C.c_int32()
+            self._check(self.lib.anx_engine_tap_kind(self._h, k, C.byref(kind), C.byref(conv)))
+            out[v[0].value] = (k, v[1].value, v[2].value, v[3].value, bool(v[4].value),
+                               conv.value if kind.value == 2 else -1)
         return out
+
+    def _ensure_tap_conv(self, conv_ordinal: int):
+        """Packs the un-folded clone of conv `conv_ordinal` (plain weight + bias) for pre-norm taps."""
+        if conv_ordinal in self._tap_convs_ready:
+            return
+        idx = self.conv_table()[conv_ordinal][0]
+        w = torch.as_tensor(self._state[f"model.{idx}.weight"]).detach().to("cpu", torch.float32).contiguous()
+        b = self._state.get(f"model.{idx}.bias")
+        b = None if b is None else torch.as_tensor(b).detach().to("cpu", torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.anx_engine_set_tap_conv(
+                self._h, conv_ordinal, C.c_void_p(w.data_ptr()), None if b is None else C.c_void_p(b.data_ptr()), 0))
+        self._tap_convs_ready.add(conv_ordinal)
 
     def forward_taps(self, x: torch.Tensor, layers, encode_only: bool = False):
         """``Unet.forward(x, layers, encode_only)`` of the reference (network.py:475-529) for tap
@@ -154,7 +174,7 @@ class Engine:
             # exported right after the launch that completes it, before later launches may reuse its region.
             done = 0
             for idx in sorted(wanted, key=lambda i: table[i][3]):
-                k, ch, lvl, last_step, is_output = table[idx]
+                k, ch, lvl, last_step, is_output, prenorm_conv = table[idx]
                 upto = min(last_step + 1, last)
                 if upto > done:
                     self._check(self.lib.anx_engine_run_steps(
@@ -164,8 +184,13 @@ class Engine:
                     taps[idx] = out
                     continue
                 t = torch.empty((n, ch, d >> lvl, h >> lvl, w >> lvl), dtype=torch.float32, device=self.device)
-                self._check(self.lib.anx_engine_export_tap(
-                    self._h, k, n, d, h, w, ws.data_ptr(), ws.numel(), t.data_ptr(), stream))
+                if prenorm_conv >= 0:       # conv(x) + bias before the norm: the conv's launch again, un-folded
+                    self._ensure_tap_conv(prenorm_conv)
+                    self._check(self.lib.anx_engine_export_prenorm_tap(
+                        self._h, k, x.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(), t.data_ptr(), stream))
+                else:
+                    self._check(self.lib.anx_engine_export_tap(
+                        self._h, k, n, d, h, w, ws.data_ptr(), ws.numel(), t.data_ptr(), stream))
                 taps[idx] = t
             if last > done:
                 self._check(self.lib.anx_engine_run_steps(
@@ -514,8 +539,7 @@ def ineligible_reason(module: nn.Module, cfg: dict, x, layers=()) -> Optional[st
         # feature taps (network.py:475-529): served when every tapped slot is a tensor the engine stores
         missing = binding_for(module, cfg).untappable(x.device, layers)
         if missing:
-            return (f"feature tap at slot {missing[0]} is not materialised by the engine "
-                    "(pre-norm conv outputs are folded into the weights)")
+            return f"feature tap at slot {missing[0]} is not a tensor the engine can hand out"
     return None
 
 

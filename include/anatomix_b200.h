@@ -258,8 +258,8 @@ int32_t anx_engine_out_channels(const anx_engine *engine);
  * can hand out the activation after Sequential slot `module_index` when it stores that tensor:
  * the last slot of every conv block (its post-norm, post-activation output), the pooling slots,
  * the Upsample slots (where the reference taps cat(skip, upsampled), network.py:545) and the last
- * conv (the network output itself).  Pre-norm conv outputs are never materialised (BatchNorm is
- * folded into the weights): a binding sends such calls down the stock torch path.
+ * conv (the network output itself).  Pre-norm conv outputs are not stored; they are served by the separate
+ * entry points below (anx_engine_tap_kind / set_tap_conv / export_prenorm_tap).
  * `anx_engine_tap_info` lists the available sites; `last_step` is the launch after which the tensor
  * is complete (run [0, last_step] with anx_engine_run_steps for `encode_only`); `is_output` marks the
  * last conv, whose tensor is the forward's fp32 output buffer itself;
@@ -287,6 +287,25 @@ anx_status anx_engine_forward_concat(anx_engine *engine, const float *in_ncdhw, 
  * models before registration / visualisation (README.md:13,49). */
 anx_status anx_channel_normalize_f32(const float *in, float *out, int64_t n, int32_t channels,
                                      int32_t d, int32_t h, int32_t w, int32_t mode, float eps, void *stream);
+
+/* PRE-norm conv taps (network.py:504-515: `layers` holding the index of an nn.Conv3d that a norm follows; the
+ * pretraining code taps these slots, pretrain_anatomix.py:383-387, supcl_model.py:275-280).  The engine never stores
+ * that tensor (eval BatchNorm is folded into the packed weights, InstanceNorm normalises in place), so such a tap is
+ * served by an un-folded clone of the conv: anx_engine_tap_kind says which sites are of this kind and which conv
+ * ordinal they belong to; anx_engine_set_tap_conv hands over that conv's plain `weight` / `bias` once (and again
+ * whenever they change); anx_engine_export_prenorm_tap re-runs the conv's launch on its still-live input tensor --
+ * call it right after anx_engine_run_steps has executed step `last_step` of the site -- and writes
+ * conv(x) + bias as fp32 NCDHW [N, channels, D>>level, H>>level, W>>level].  `in_ncdhw` is the forward's input
+ * (read again only when the tapped conv is the stem).  Not offered for the decoder conv that runs as two launches
+ * (use an engine created with ANX_FLAG_NO_UPCONV for a tap there). */
+enum { ANX_TAP_STORED = 0, ANX_TAP_OUTPUT = 1, ANX_TAP_PRENORM = 2 };
+anx_status anx_engine_tap_kind(const anx_engine *engine, int32_t k, int32_t *kind, int32_t *conv_ordinal);
+anx_status anx_engine_set_tap_conv(anx_engine *engine, int32_t conv_ordinal, const float *weight,
+                                   const float *bias, int32_t location);
+anx_status anx_engine_export_prenorm_tap(anx_engine *engine, int32_t k, const float *in_ncdhw,
+                                         int32_t n, int32_t d, int32_t h, int32_t w,
+                                         void *workspace, size_t workspace_bytes,
+                                         float *out_ncdhw, void *stream);
 
 /* out = scale * avg_pool3d(in, k, stride=k) on a contiguous fp32 [nc, D, H, W] device tensor (floor
  * mode), on the current device.  Replaces: `pred * downscale_feat_scalar` followed by

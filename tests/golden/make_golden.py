@@ -102,6 +102,30 @@ def mint_g8(Unet):
         np.savez_compressed(os.path.join(HERE, "g9_94m_64_w30.npz"), out_s4=sub(y, 4), mom=moments(y))
 
 
+def mint_g10(Unet, sd):
+    """G10: PRE-norm conv taps (network.py:504-515: `layers` holding conv slots, as the pretraining code does): the
+    stem, encoder / bottleneck / decoder convs at every level incl. the level-0 decoder conv the engine may run as two
+    launches, for the 6M model; plus the 94M config's stem and a deep conv (InstanceNorm: bias-carrying convs)."""
+    m6 = Unet(**CFG_6M); m6.load_state_dict(sd, strict=True); m6.eval()
+    ids = [0, 3, 6, 10, 27, 34, 38, 52, 59, 62]
+    with torch.no_grad():
+        x = rand_input((1, 1, 32, 32, 32), 5)
+        y, taps = m6(x, layers=ids)
+        g = {"tap_ids": np.array(ids), "out_s2": sub(y, 2)}
+        for i, t in zip(ids, taps):
+            g[f"tap{i}"] = sub(t, 2) if t.shape[-1] > 4 else t.numpy()
+    torch.manual_seed(0)
+    m94 = Unet(**CFG_94M).eval()
+    ids94 = [0, 3, 38, 76]
+    with torch.no_grad():
+        x = rand_input((1, 1, 64, 64, 64), 0)
+        y, taps = m94(x, layers=ids94)
+        g["tap_ids_94m"] = np.array(ids94)
+        for i, t in zip(ids94, taps):
+            g[f"m94_tap{i}"] = sub(t, 4) if t.shape[-1] > 4 else t.numpy()
+    np.savez_compressed(os.path.join(HERE, "g10_prenorm_taps.npz"), **g)
+
+
 def main():
     sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.abspath(os.path.join(HERE, "..", ".."))]
     sys.path.insert(0, REF)
@@ -109,6 +133,10 @@ def main():
     import anatomix.model.network as net
     assert net.__file__.startswith(REF), net.__file__
     torch.set_num_threads(os.cpu_count())
+    if sys.argv[1:] == ["g10"]:            # add G10 without re-minting the others
+        mint_g10(Unet, torch.load(os.path.join(REF, "model-weights", "anatomix.pth"), map_location="cpu"))
+        write_manifest()
+        return
     if sys.argv[1:] == ["g8"]:             # add G8 / G9 without re-minting the others
         mint_g8(Unet)
         write_manifest()
@@ -176,6 +204,7 @@ def main():
 
     mint_g7(Unet, sd)
     mint_g8(Unet)
+    mint_g10(Unet, sd)
     write_manifest()
 
 

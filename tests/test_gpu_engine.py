@@ -416,8 +416,8 @@ def test_feature_taps_on_the_engine_g7(state_6m):
     with torch.no_grad():
         assert m.engine_ineligible_reason(x.cuda(), ids) is None
         y, taps = m(x.cuda(), layers=ids)
-        assert "not materialised" in m.engine_ineligible_reason(x.cuda(), [8, 59])     # pre-norm conv output
-        y_t, taps_t = m(x.cuda(), layers=[8, 59])                                      # ... stock torch path
+        assert m.engine_ineligible_reason(x.cuda(), [8, 59]) is None     # slot 59: a pre-norm conv output, engine too
+        y_t, taps_t = m(x.cuda(), layers=[8, 59])
     torch.cuda.synchronize()
     assert len(taps) == len(ids) and taps[-1] is y                       # slot 65 is the output itself
     _, emu = O.unet_forward(CFG_6M, state_6m, x, layers=ids, engine_rounding=True)
@@ -451,9 +451,13 @@ def test_feature_taps_instance_norm_network():
     y, taps = eng.forward_taps(x.cuda(), ids)
     torch.cuda.synchronize()
     _, emu = O.unet_forward(cfg, state, x, layers=ids, engine_rounding=True)
-    for i, t, e in zip(ids, taps, emu):
+    _, ref = O.unet_forward(cfg, state, x, layers=ids)
+    for i, t, e, f in zip(ids, taps, emu, ref):
         assert t.shape == e.shape, (i, t.shape, e.shape)
-        r = rel_l2(t.float().cpu(), e)
+        # pre-norm conv slots (conv + bias, re-evaluated by an un-folded clone) have no counterpart among the tensors the
+        # emulation models: they are held to the fp32 oracle; stored tensors to the 16-bit emulation
+        want = f if table[i][5] >= 0 else e
+        r = rel_l2(t.float().cpu(), want)
         assert r <= 2e-2, f"tap {i}: rel-L2 {r:.3e}"
 
 
@@ -807,3 +811,70 @@ def test_row_form_stem_matches_tile_form_stem(shape, halo):
     got = bufs[0][:, :, 1:-1, 1:-1, 1:w + 1].permute(0, 1, 5, 2, 3, 4).reshape(n, 16, d, h, w)
     r = rel_l2(got.cpu(), want.cpu())
     assert r < 4e-3, f"row-form stem vs fp32 conv: rel-L2 {r:.3e} (bf16 storage alone is ~2e-3)"
+
+
+def test_prenorm_conv_taps_g10(state_6m):
+    """Taps at conv slots that a norm follows (network.py:504-515; the pretraining defaults): the reference returns the
+    conv output BEFORE the norm.  The engine re-evaluates it with an un-folded clone of the conv right after that
+    conv's launch (anx_engine_set_tap_conv / anx_engine_export_prenorm_tap).  Golden G10 from the unmodified reference."""
+    from anatomix_b200 import Unet
+    g = golden("g10_prenorm_taps.npz")
+    ids = [int(i) for i in g["tap_ids"]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**CFG_6M)
+    m.load_state_dict(state_6m)
+    m = m.cuda().eval()
+    x = rand_input((1, 1, 32, 32, 32), 5)
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(x.cuda(), ids) is None
+        y, taps = m(x.cuda(), layers=ids)
+        # mixed with stored tensors and with encode_only
+        y2, taps2 = m(x.cuda(), layers=[3, 8, 9, 10])
+        only = m(x.cuda(), layers=[0, 10], encode_only=True)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu()[:, :, ::2, ::2, ::2], torch.from_numpy(g["out_s2"])) <= LOOSE_REL
+    for i, t in zip(ids, taps):
+        got = t.float().cpu()
+        want = torch.from_numpy(g[f"tap{i}"])
+        sub = got[:, :, ::2, ::2, ::2] if got.shape[-1] > 4 else got
+        assert sub.shape == want.shape, (i, sub.shape, want.shape)
+        r = rel_l2(sub, want)
+        print(f"pre-norm tap {i}: rel-L2 {r:.3e}")
+        assert r <= LOOSE_REL, f"pre-norm tap {i}: rel-L2 {r:.3e} vs reference golden"
+    assert torch.equal(taps2[0], taps[1]) and torch.equal(taps2[3], taps[3]) and len(taps2) == 4
+    assert len(only) == 2 and torch.equal(only[0], taps[0]) and torch.equal(only[1], taps[3])
+    # weights edited in place: the clone follows the re-pack
+    with torch.no_grad():
+        m.model[3].weight.mul_(2.0)
+        _, t2 = m(x.cuda(), layers=[3])
+    assert rel_l2(t2[0].cpu(), 2 * taps[1].cpu()) < 1e-2
+    # row-kernel shape (128 wide): the clones of the stem and of the 16 -> 16 convs run on the row kernels
+    xw = rand_input((1, 1, 32, 32, 128), 6)
+    with torch.no_grad():
+        m.model[3].weight.mul_(0.5)
+        _, tw = m(xw.cuda(), layers=[0, 3, 62])
+    _, want = O.unet_forward(CFG_6M, state_6m, xw, layers=[0, 3, 62])
+    for i, a, b in zip([0, 3, 62], tw, want):
+        assert rel_l2(a.cpu(), b) <= LOOSE_REL, f"pre-norm tap {i} at 128 wide: {rel_l2(a.cpu(), b):.3e}"
+
+
+def test_prenorm_conv_taps_instance_norm_94m():
+    cfg, sd = _seeded_94m()
+    g = golden("g10_prenorm_taps.npz")
+    ids = [int(i) for i in g["tap_ids_94m"]]
+    from anatomix_b200 import Unet
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Unet(**cfg)
+    m = m.cuda().eval()
+    x = rand_input((1, 1, 64, 64, 64), 0)
+    with torch.no_grad():
+        assert m.engine_ineligible_reason(x.cuda(), ids) is None
+        _, taps = m(x.cuda(), layers=ids)
+    for i, t in zip(ids, taps):
+        got = t.float().cpu()
+        want = torch.from_numpy(g[f"m94_tap{i}"])
+        sub = got[:, :, ::4, ::4, ::4] if got.shape[-1] > 4 else got
+        r = rel_l2(sub, want)
+        print(f"94M pre-norm tap {i}: rel-L2 {r:.3e}")
+        assert r <= LOOSE_REL, f"94M pre-norm tap {i}: rel-L2 {r:.3e}"

@@ -80,6 +80,17 @@ def test_g9_94m_with_conv_weights_scaled_by_30():
     np.testing.assert_allclose(y[:, :, ::4, ::4, ::4].numpy(), g["out_s4"], atol=5e-4, rtol=1e-3)
 
 
+def test_g10_prenorm_conv_taps(state_6m):
+    """Golden G10: taps at conv slots that a norm follows hold the PRE-norm conv output (network.py:504-515)."""
+    g = golden("g10_prenorm_taps.npz")
+    ids = [int(i) for i in g["tap_ids"]]
+    y, taps = O.unet_forward(CFG_6M, state_6m, rand_input((1, 1, 32, 32, 32), 5), layers=ids)
+    np.testing.assert_allclose(sub(y, 2), g["out_s2"], atol=TOL, rtol=1e-4)
+    for i, t in zip(ids, taps):
+        got = sub(t, 2) if t.shape[-1] > 4 else t.numpy()
+        np.testing.assert_allclose(got, g[f"tap{i}"], atol=TOL, rtol=1e-4, err_msg=f"tap {i}")
+
+
 def test_g5_train_mode_batch_stats(state_6m):
     g = golden("g5_6m_train.npz")
     y = O.unet_forward(CFG_6M, state_6m, rand_input((1, 1, 32, 32, 32), 0), training=True)
