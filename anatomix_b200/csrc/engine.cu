@@ -900,6 +900,13 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         if (!force_simt && p.geoms[s.conv].fuse_pool) return ANX_OK;   // already written by the conv's epilogue
         ActView src = view_of(e, p, s.src_buf, 0), dst = view_of(e, p, s.dst_buf, 0);
         const size_t items = (size_t)p.N * s.groups * dst.D * dst.H * dst.W;
+        if (dst.D >= 4 && dst.H >= 4 && dst.W >= 32 && dst.D <= 65535 && (size_t)p.N * s.groups <= 65535) {
+            const dim3 grid(dst.H, dst.D, p.N * s.groups);
+            const int threads = std::min(128, (dst.W + 31) / 32 * 32);
+            if (e->dt == DT_BF16) pool2_grid_kernel<DT_BF16><<<grid, threads, 0, st>>>(src, dst, s.groups, e->desc.pool_kind);
+            else pool2_grid_kernel<DT_FP16><<<grid, threads, 0, st>>>(src, dst, s.groups, e->desc.pool_kind);
+            break;
+        }
         pool2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups,
                                                                            e->desc.pool_kind, e->dt);
         break;
@@ -914,11 +921,13 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
                 upsample2_nearest_kernel<<<grid_for(items / 4, 256, e->num_sms, 32), 256, 0, st>>>(src, dst, p.N, s.groups);
         }
         else if (dst.D >= 4 && dst.H >= 4 && dst.W >= 32 && dst.D <= 65535 && (size_t)p.N * s.groups <= 65535) {
-            const dim3 grid(dst.H, dst.D, p.N * s.groups);
+            // one thread per low-resolution voxel (27 loads per 8 outputs, separable weights)
+            const dim3 grid(src.H, src.D, p.N * s.groups);
+            const int threads = std::min(64, (src.W + 31) / 32 * 32);
             if (e->dt == DT_BF16)
-                upsample2_tri_grid_kernel<DT_BF16><<<grid, std::min(128, dst.W), 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+                upsample2_tri_block_kernel<DT_BF16><<<grid, threads, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
             else
-                upsample2_tri_grid_kernel<DT_FP16><<<grid, std::min(128, dst.W), 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
+                upsample2_tri_block_kernel<DT_FP16><<<grid, threads, 0, st>>>(src, dst, s.groups, e->slab_lower, e->slab_upper);
         }
         else
             upsample2_kernel<<<grid_for(items, 256, e->num_sms, 32), 256, 0, st>>>(
