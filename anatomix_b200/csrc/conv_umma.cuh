@@ -52,6 +52,9 @@ struct UmmaShared {          // lives behind the A / B rings in dynamic shared m
     uint32_t pad[3];
     float shift[1024];       // per-channel accumulator seed (folded BN shift / bias), all splits
 };
+// EPI_STATS on thin layers (ConvGeom::stats_acc): per-warp instance-norm sums of the current sample, in an extra
+// region right behind UmmaShared that only such launches allocate
+constexpr uint32_t STATS_ACC_BYTES = EPI_WARPS * 2 * STATS_ACC_MAX_COLS * sizeof(double);
 
 struct TileCoord { int n, z0, y0, x0, split; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvGeom &g, int tile) {
@@ -290,9 +293,25 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
         tc_fence_before();
         for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
 
+        // EPI_STATS on thin layers: sums are kept per warp in shared memory and flushed once per sample
+        double *my_acc = nullptr;
+        int acc_n = -1;
+        if constexpr (MODE == EPI_STATS) {
+            if (g.stats_acc) {
+                my_acc = reinterpret_cast<double *>(sh + 1) + (warp - 2) * 2 * STATS_ACC_MAX_COLS;
+                for (int i = lane; i < 2 * g.ncols; i += 32) my_acc[i] = 0.0;
+                __syncwarp();
+            }
+        }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const EpiTile et = epi_tile_of(tile);
+            if constexpr (MODE == EPI_STATS) {
+                if (my_acc && et.n != acc_n) {
+                    if (acc_n >= 0) warp_stats_flush(my_acc, chunks, ep.stats, ep.stats_stride, acc_n);
+                    acc_n = et.n;
+                }
+            }
             const uint32_t s = it % g.acc_stages;
             const int next = tile + g.acc_stages * (int)gridDim.x;   // the tile that reuses this accumulator stage
             const bool next_valid = SEEDED && next < g.total_tiles;
@@ -301,10 +320,13 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvGeom g,
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 6);
             tc_fence_after();
             umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift + (next % g.n_splits) * g.ncols, half,
-                                       g.bz, g.ncols, g.D, en, next_valid);
+                                       g.bz, g.ncols, g.D, en, next_valid, my_acc);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);
+        }
+        if constexpr (MODE == EPI_STATS) {
+            if (my_acc && acc_n >= 0) warp_stats_flush(my_acc, chunks, ep.stats, ep.stats_stride, acc_n);
         }
     }
 

@@ -558,7 +558,11 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.a_stage_bytes = 2 * g.a_lbo;
     g.b_rows = c.fold ? 3 * g.ncols : g.ncols;
     g.b_stage_bytes = 9 * 32 * g.b_rows;
-    const size_t budget = (size_t)e->max_smem - sizeof(UmmaShared) - 1024;
+    // InstanceNorm statistics of thin layers are accumulated per CTA in shared memory (one flush per sample instead
+    // of one double atomic per warp, chunk and tile)
+    g.stats_acc = (c.inorm && g.ncols <= STATS_ACC_MAX_COLS && c.n_splits == 1) ? 1 : 0;
+    const size_t shared_tail = sizeof(UmmaShared) + (g.stats_acc ? STATS_ACC_BYTES : 0);
+    const size_t budget = (size_t)e->max_smem - shared_tail - 1024;
     g.a_stages = 3;
     g.b_stages = 2;
     const size_t b_reserve = (g.b_static ? 1u : 2u) * (size_t)g.b_stage_bytes;
@@ -568,8 +572,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.b_stages = std::min(g.b_stages, std::max(2, 2 * g.groups));
     if (g.b_static) g.b_stages = std::min(g.b_stages, 1);
     if (const char *ab = exp_env("ANX_ABLATE")) g.ablate = (uint32_t)atoi(ab);
-    g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes +
-                              sizeof(UmmaShared));
+    g.smem_bytes = (uint32_t)((size_t)g.a_stages * g.a_stage_bytes + (size_t)g.b_stages * g.b_stage_bytes + shared_tail);
     // Low-resolution half of a decoder conv: each tap's MMA covers just the span of its parities (trim_span); when the
     // compact tiles of the whole layer fit next to the A ring they stay resident in shared memory, loaded once per CTA
     // instead of streaming 221 KB of (mostly zero) slabs from L2 for every tile.
@@ -796,8 +799,9 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             g.brick_bytes = (uint32_t)(c.cin * (g.bz + 2) * HALO_Y * STEM_BRICK_X * 4);
             g.a_tile_bytes = (uint32_t)(g.kq * 2 * 128 * 16);
             g.b_bytes = (uint32_t)(g.kq * 2 * 3 * g.ncols * 16);
+            g.stats_acc = (ep.stats && g.ncols <= STATS_ACC_MAX_COLS) ? 1 : 0;
             g.smem_bytes = stem_bricks(g.kq) * ((g.brick_bytes + 127) & ~127u) + stem_a_slots(g.kq) * 2 * g.a_tile_bytes + 2 * g.b_bytes +
-                           (uint32_t)sizeof(StemShared);
+                           (uint32_t)sizeof(StemShared) + (g.stats_acc ? STATS_ACC_BYTES : 0);
             if (g.smem_bytes > (uint32_t)e->max_smem)
                 return e->fail(ANX_ERR_UNSUPPORTED, "stem tile does not fit shared memory (%u bytes)", g.smem_bytes);
             CUtensorMap tm;

@@ -64,7 +64,12 @@ __device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b, int dt) {
 // `s` and 16 partial sums of squares `q` (its own voxels).  A butterfly
 // reduce-scatter (31 shuffles for the 32 values) leaves lane l with the warp total of
 // value l, which it adds to `stats16[(l & 15) * 2 + (l >> 4)]` in double precision.
-__device__ __forceinline__ void warp_stats_add(const float *s, const float *q, double *stats16) {
+// `acc` (optional): this warp's private 32-double row in shared memory for the chunk -- lane l adds its total there
+// instead of issuing a global atomic; the kernel flushes the rows when the sample changes and at its end
+// (STATS_ACC_MAX_COLS).  With one atomic per warp, chunk and TILE the thin 128^3 layers issued 4 M double atomics
+// onto 256 addresses per launch.
+constexpr int STATS_ACC_MAX_COLS = 64;      // per-CTA accumulation rows exist for layers of at most this many columns
+__device__ __forceinline__ void warp_stats_add(const float *s, const float *q, double *stats16, double *acc = nullptr) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { v[i] = s[i]; v[16 + i] = q[i]; }
@@ -79,7 +84,18 @@ __device__ __forceinline__ void warp_stats_add(const float *s, const float *q, d
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
         }
     }
-    atomicAdd(stats16 + (lane & 15) * 2 + (lane >> 4), (double)v[0]);
+    if (acc) acc[lane] += (double)v[0];
+    else atomicAdd(stats16 + (lane & 15) * 2 + (lane >> 4), (double)v[0]);
+}
+// Adds one warp's accumulated rows (`chunks` x 32 doubles, layout of warp_stats_add) for sample n to the global
+// sums and clears them.
+__device__ __forceinline__ void warp_stats_flush(double *acc, int chunks, double *stats, int stats_stride, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int cb = 0; cb < chunks; ++cb) {
+        const double v = acc[cb * 32 + lane];
+        if (v != 0.0) atomicAdd(stats + ((size_t)n * stats_stride + cb * 16) * 2 + (lane & 15) * 2 + (lane >> 4), v);
+        acc[cb * 32 + lane] = 0.0;
+    }
 }
 
 // Padded-coordinate targets of interior coordinate v on an axis of size S:

@@ -54,6 +54,7 @@ struct StemGeom {
     uint32_t a_tile_bytes;                // kq * 2 * 128 * 16   (one of hi / lo)
     uint32_t b_bytes;                     // kq * 2 * (3*ncols) * 16 (one of hi / lo)
     uint32_t smem_bytes;
+    int stats_acc;                        // EPI_STATS: per-warp sums in shared memory behind StemShared (STATS_ACC_BYTES more)
     int dbg_shift;                        // experiments only
     uint32_t ablate;                      // timing experiments (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A build, 8 no brick load
 };
@@ -267,9 +268,24 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
         tc_fence_before();
         for (int s = 0; s < g.acc_stages; ++s) mbar_arrive(&sh->tmem_empty[s]);
 
+        double *my_acc = nullptr;
+        int acc_n = -1;
+        if constexpr (MODE == EPI_STATS) {
+            if (g.stats_acc) {               // region behind StemShared, allocated by EPI_STATS launches only
+                my_acc = reinterpret_cast<double *>(sh + 1) + (warp - 2) * 2 * STATS_ACC_MAX_COLS;
+                for (int i = lane; i < 2 * g.ncols; i += 32) my_acc[i] = 0.0;
+                __syncwarp();
+            }
+        }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const int n = tile / g.tiles_per_sample;
+            if constexpr (MODE == EPI_STATS) {
+                if (my_acc && n != acc_n) {
+                    if (acc_n >= 0) warp_stats_flush(my_acc, chunks, ep.stats, ep.stats_stride, acc_n);
+                    acc_n = n;
+                }
+            }
             int rr = tile - n * g.tiles_per_sample;
             const int tz = rr / (g.tiles_y * g.tiles_x);
             rr -= tz * g.tiles_y * g.tiles_x;
@@ -282,10 +298,13 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const StemGeom g, 
             et.store = !(ANX_ABL(g, 2));
             mbar_wait(&sh->tmem_full[s], (it / g.acc_stages) & 1, 17);
             tc_fence_after();
-            umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false);
+            umma_epilogue_tile<MODE>(ep, et, lane_base + s * acc_cols, sh->shift, half, g.bz, g.ncols, g.D, et, false, my_acc);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sh->tmem_empty[s]);
+        }
+        if constexpr (MODE == EPI_STATS) {
+            if (my_acc && acc_n >= 0) warp_stats_flush(my_acc, chunks, ep.stats, ep.stats_stride, acc_n);
         }
     }
 

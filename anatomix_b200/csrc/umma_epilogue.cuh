@@ -69,10 +69,12 @@ enum EpiMode : int {
 constexpr int HEAD_SMEM_OFFSET = 32;   // floats behind the channel shift in shared memory where the head lives
 
 // `next` / `next_valid`: the tile that will reuse this accumulator stage (seeded kernels only).
+// `stats_acc`: EPI_STATS only -- this warp's shared-memory accumulation rows (ncols / 16 x 32 doubles), or nullptr to
+// add to the global sums directly.
 template <int MODE>
 __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const EpiTile &t, uint32_t acc,
                                                    const float *seed, const PlaneSplit &half, int bz, int ncols, int D,
-                                                   const EpiTile &next, bool next_valid) {
+                                                   const EpiTile &next, bool next_valid, double *stats_acc = nullptr) {
     const int Dd = ep.dst.D, Hh = ep.dst.H, Ww = ep.dst.W;
     const size_t plane = (size_t)(Hh + 2) * ep.dst.pitch;      // uint4 units
     const size_t gstride = (size_t)(Dd + 2) * plane;
@@ -303,7 +305,8 @@ __device__ __forceinline__ void umma_epilogue_tile(const Epilogue &ep, const Epi
         }
         if constexpr (MODE == EPI_STATS) {   // whole warp converged: the loops above have warp-uniform trip counts
             __syncwarp();
-            warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2);
+            warp_stats_add(s16, q16, ep.stats + ((size_t)t.n * ep.stats_stride + c0) * 2,
+                           stats_acc ? stats_acc + cb * 32 : nullptr);
         }
     }
 }
