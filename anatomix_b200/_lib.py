@@ -44,6 +44,7 @@ EXPORTS = [
     "anx_push_to_peers", "anx_engine_forward_slab", "anx_engine_forward_host_ex",
     "anx_engine_forward_concat", "anx_channel_normalize_f32",
     "anx_engine_tap_kind", "anx_engine_set_tap_conv", "anx_engine_export_prenorm_tap",
+    "anx_engine_forward_host_pipelined", "anx_engine_host_wait",
 ]
 
 
@@ -139,6 +140,10 @@ def load():
     lib.anx_engine_set_tap_conv.restype = i32
     lib.anx_engine_export_prenorm_tap.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, sz, vp, vp]
     lib.anx_engine_export_prenorm_tap.restype = i32
+    lib.anx_engine_forward_host_pipelined.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.anx_engine_forward_host_pipelined.restype = i32
+    lib.anx_engine_host_wait.argtypes = [vp, vp]
+    lib.anx_engine_host_wait.restype = i32
     lib.anx_engine_row_layout.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.anx_engine_row_layout.restype = i32
     lib.anx_engine_set_head.argtypes = [vp, i32, vp, vp, i32]

@@ -193,6 +193,12 @@ struct anx_engine {
     std::mutex host_mu;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in[8] = {nullptr}, ev_out[8] = {nullptr};
+    // pipelined host-buffer forwards (anx_engine_forward_host_pipelined): last download that read a given dev_out
+    // buffer (two buffer sets alternate), and whether `ev_join` marks downloads the caller has not waited for yet
+    void *pipe_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pipe_done[2] = {nullptr, nullptr};
+    int pipe_next = 0;
+    bool pipe_pending = false;
     // copy-engine push of the feature all-gather (anx_push_to_peers): one stream per destination
     cudaStream_t push_stream[8] = {nullptr};
     cudaEvent_t ev_push_fork = nullptr, ev_push_done[8] = {nullptr};
@@ -1069,6 +1075,8 @@ void anx_engine_destroy(anx_engine *e) {
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    for (int i = 0; i < 2; ++i)
+        if (e->ev_pipe_done[i]) cudaEventDestroy(e->ev_pipe_done[i]);
     for (int i = 0; i < 8; ++i) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
@@ -1642,9 +1650,36 @@ anx_status anx_engine_forward_host(anx_engine *e, const float *in_host, float *o
                                       workspace, ws_bytes, stream);
 }
 
+static anx_status forward_host_impl(anx_engine *e, const float *in_host, void *out_host_v, int32_t payload, int32_t n,
+                                    int32_t d, int32_t h, int32_t w, float *dev_in, void *dev_out_v, void *workspace,
+                                    size_t ws_bytes, void *stream, bool pipelined);
+
 anx_status anx_engine_forward_host_ex(anx_engine *e, const float *in_host, void *out_host_v, int32_t payload,
                                       int32_t n, int32_t d, int32_t h, int32_t w, float *dev_in, void *dev_out_v,
                                       void *workspace, size_t ws_bytes, void *stream) {
+    return forward_host_impl(e, in_host, out_host_v, payload, n, d, h, w, dev_in, dev_out_v, workspace, ws_bytes, stream, false);
+}
+
+anx_status anx_engine_forward_host_pipelined(anx_engine *e, const float *in_host, void *out_host_v, int32_t payload,
+                                             int32_t n, int32_t d, int32_t h, int32_t w, float *dev_in,
+                                             void *dev_out_v, void *workspace, size_t ws_bytes, void *stream) {
+    return forward_host_impl(e, in_host, out_host_v, payload, n, d, h, w, dev_in, dev_out_v, workspace, ws_bytes, stream, true);
+}
+
+anx_status anx_engine_host_wait(anx_engine *e, void *stream) {
+    if (!e) return ANX_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(e->host_mu);
+    if (e->pipe_pending) {
+        ANX_CUDA(e, cudaSetDevice(e->desc.device));
+        ANX_CUDA(e, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), e->ev_join, 0));
+        e->pipe_pending = false;
+    }
+    return ANX_OK;
+}
+
+static anx_status forward_host_impl(anx_engine *e, const float *in_host, void *out_host_v, int32_t payload, int32_t n,
+                                    int32_t d, int32_t h, int32_t w, float *dev_in, void *dev_out_v, void *workspace,
+                                    size_t ws_bytes, void *stream, bool pipelined) {
     if (!e) return ANX_ERR_BAD_ARG;
     if (payload != ANX_PAYLOAD_F32_NCDHW && payload != ANX_PAYLOAD_CL16) return e->fail(ANX_ERR_BAD_ARG, "bad payload kind");
     char *out_host = static_cast<char *>(out_host_v), *dev_out = static_cast<char *>(dev_out_v);
@@ -1662,7 +1697,14 @@ anx_status anx_engine_forward_host_ex(anx_engine *e, const float *in_host, void 
             ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
             ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < 2; ++i) ANX_CUDA(e, cudaEventCreateWithFlags(&e->ev_pipe_done[i], cudaEventDisableTiming));
     }
+    // A download issued by an earlier pipelined call may still be reading this dev_out buffer: the convs of this call
+    // (which overwrite it) wait for that download.  Two buffer sets used alternately never wait on each other.
+    int slot = -1;
+    for (int i = 0; i < 2; ++i)
+        if (e->pipe_out[i] == dev_out_v) slot = i;
+    if (slot >= 0) ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_pipe_done[slot], 0));
     // Three-stage pipeline over chunks of the batch: the upload of chunk i+1 and the download of
     // chunk i-1 run on their own streams while chunk i computes on the caller's stream.  The
     // download (output_nc/input_nc times larger than the upload) is what bounds the call.
@@ -1692,7 +1734,16 @@ anx_status anx_engine_forward_host_ex(anx_engine *e, const float *in_host, void 
         lo += cnt;
     }
     ANX_CUDA(e, cudaEventRecord(e->ev_join, e->d2h_stream));
-    ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));   // the caller's stream completes after the last download
+    if (pipelined) {
+        // the caller's stream does NOT wait for the download: the next call's upload and convs overlap it;
+        // anx_engine_host_wait joins.  Remember which download last read this dev_out buffer.
+        if (slot < 0) { slot = e->pipe_next; e->pipe_next ^= 1; e->pipe_out[slot] = dev_out_v; }
+        ANX_CUDA(e, cudaEventRecord(e->ev_pipe_done[slot], e->d2h_stream));
+        e->pipe_pending = true;
+    } else {
+        ANX_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));   // the caller's stream completes after the last download
+        e->pipe_pending = false;
+    }
     return ANX_OK;
 }
 

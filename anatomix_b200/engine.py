@@ -389,6 +389,30 @@ class Engine:
                 self._h, x_host.data_ptr(), out_host.data_ptr(), _lib.PAYLOAD_CL16, n, d, h, w, dev_in.data_ptr(),
                 dev_out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
 
+    def forward_host_pipelined(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
+                               dev_out: torch.Tensor):
+        """`forward_host` for back-to-back calls: the current stream does not wait for the download, so the next
+        call's upload and convs overlap it (anx_engine_forward_host_pipelined).  Alternate two ``(dev_out, out_host)``
+        sets; results are complete after `host_wait()` + a stream synchronisation."""
+        n, _, d, h, w = x_host.shape
+        for t, shape, what in ((x_host, (n, self.input_nc, d, h, w), "x_host"),
+                               (out_host, (n, self.output_nc, d, h, w), "out_host")):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"`{what}` must be a contiguous fp32 CPU tensor of shape {shape}")
+        self._check_out(dev_in, (n, self.input_nc, d, h, w), "dev_in")
+        self._check_out(dev_out, (n, self.output_nc, d, h, w), "dev_out")
+        ws = self.workspace(n, d, h, w)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.anx_engine_forward_host_pipelined(
+                self._h, x_host.data_ptr(), out_host.data_ptr(), _lib.PAYLOAD_F32_NCDHW, n, d, h, w,
+                dev_in.data_ptr(), dev_out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+
+    def host_wait(self):
+        """The current stream waits for every download issued by `forward_host_pipelined` so far."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.anx_engine_host_wait(self._h, torch.cuda.current_stream(self.device).cuda_stream))
+
     def forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor, dev_in: torch.Tensor,
                      dev_out: torch.Tensor):
         """End-to-end call on (pinned) host buffers; see anx_engine_forward_host."""

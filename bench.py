@@ -621,7 +621,36 @@ def main():
     y_host = torch.empty((B, 16, VOL, VOL, VOL), dtype=torch.float32).pin_memory()
     dev_in = torch.empty((B, 1, VOL, VOL, VOL), dtype=torch.float32, device=dev)
     e2e_steps = max(3, min(args.steps, 10))
-    ms_e2e = tm.run(lambda i: eng.forward_host(x_host[i % 2], y_host, dev_in, out), e2e_steps, 1) * e2e_steps
+    ms_e2e_single = tm.run(lambda i: eng.forward_host(x_host[i % 2], y_host, dev_in, out), e2e_steps, 1)
+    # back-to-back calls the way a throughput caller issues them: two {device output, host output} sets alternate,
+    # the download of call k overlaps the upload and convs of call k + 1 (anx_engine_forward_host_pipelined); the
+    # timed region ends after anx_engine_host_wait + synchronize, i.e. with every result in host memory
+    y_host2 = torch.empty_like(y_host).pin_memory()
+    out2 = torch.empty_like(out)
+    sets = [(y_host, out), (y_host2, out2)]
+
+    def e2e_call(i):
+        yh, od = sets[i % 2]
+        eng.forward_host_pipelined(x_host[i % 2], yh, dev_in, od)
+    e2e_call(0)
+    eng.host_wait()
+    tm.barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for i in range(e2e_steps):
+        e2e_call(i)
+    eng.host_wait()
+    eb.record()
+    tm.barrier()
+    ms_e2e = ea.elapsed_time(eb)
+    del y_host2, out2
+    # the link itself: a plain pinned device -> host copy of one step's fp32 output (what bounds the e2e number)
+    def d2h(i):
+        y_host.copy_(out, non_blocking=True)
+    ms_d2h = tm.run(d2h, 3, 1)
+    pcie = {"d2h_gbs_plain_copy": out.numel() * 4 / ms_d2h / 1e6,
+            "e2e_bound_volumes_per_s": world * B * 1e3 / ms_d2h,
+            "note": "cudaMemcpyAsync of one step's fp32 features (pinned host memory), all ranks at once"}
     # the same call with the opt-in 16-bit channels-last payload (half the download)
     e2e_cl16 = None
     try:
@@ -639,11 +668,11 @@ def main():
     # ---- per-launch device times (CUDA events around every launch of one forward), averaged
     acc, order = launch_profile(eng, xs)
 
-    times = torch.tensor([ms_total, ms_e2e, headline_gather["ms_total"] if headline_gather else 0.0],
+    times = torch.tensor([ms_total, ms_e2e, headline_gather["ms_total"] if headline_gather else 0.0, ms_e2e_single],
                          dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_gather_total = times.tolist()
+    ms_total, ms_e2e, ms_gather_total, ms_e2e_single = times.tolist()
 
     extras = {}
     if not args.no_extras and B == BATCH:
@@ -683,8 +712,14 @@ def main():
                        f"({eng.workspace_bytes(B, VOL, VOL, VOL) >> 20} MiB) exceed the 126 MB L2",
                        "parallelism": par},
             "e2e": {"value": world * B * e2e_steps / (ms_e2e / 1e3), "unit": "volumes/s",
-                    "h2d_bytes_per_step": B * VOL ** 3 * 4, "d2h_bytes_per_step": B * 16 * VOL ** 3 * 4},
+                    "h2d_bytes_per_step": B * VOL ** 3 * 4, "d2h_bytes_per_step": B * 16 * VOL ** 3 * 4,
+                    "how": "anx_engine_forward_host_pipelined: pinned host input -> H2D -> forward -> D2H into pinned host "
+                           "memory every step, back-to-back calls on two alternating output buffer sets; timed to "
+                           "anx_engine_host_wait + synchronize (every result in host memory)"},
+            "e2e_single_call": {"value": world * B * 1e3 / ms_e2e_single, "unit": "volumes/s",
+                                "how": "anx_engine_forward_host: each call completes its download before the next starts"},
             "e2e_cl16": e2e_cl16,
+            "e2e_link": pcie,
             "gpu_launches": eng.launches_per_forward(B, VOL, VOL, VOL) * args.steps,
             "clocks": clocks,
             "roofline": roofline_block(acc, order, GFLOP_6M, GFLOP_6M_STEM, MB_6M, CEIL_6M, B, value_compute / world,

@@ -239,6 +239,18 @@ anx_status anx_engine_forward_host_ex(anx_engine *engine, const float *in_host, 
                                       float *dev_in, void *dev_out,
                                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Pipelined form for back-to-back calls: like anx_engine_forward_host_ex, but `stream` does NOT wait for the download,
+ * so the upload and the convs of the next call overlap it and the PCIe link never idles.  Results (of every call so
+ * far) are complete once `stream` has passed an anx_engine_host_wait.  Alternate two {dev_out, out_host} sets: a call
+ * waits for the earlier download that still reads the dev_out buffer it is about to overwrite (with a single set
+ * the calls simply serialise).  The host input buffer must stay untouched until its upload has run, as with any
+ * asynchronous copy. */
+anx_status anx_engine_forward_host_pipelined(anx_engine *engine, const float *in_host, void *out_host,
+                                             int32_t payload, int32_t n, int32_t d, int32_t h, int32_t w,
+                                             float *dev_in, void *dev_out,
+                                             void *workspace, size_t workspace_bytes, void *stream);
+anx_status anx_engine_host_wait(anx_engine *engine, void *stream);
+
 /* ---- rows next to the hot path -------------------------------------------
  *
  * Linear head fused into the last conv's epilogue: out[k] = bias[k] + sum_c weight[k][c] * y[c]

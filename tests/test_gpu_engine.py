@@ -878,3 +878,27 @@ def test_prenorm_conv_taps_instance_norm_94m():
         r = rel_l2(sub, want)
         print(f"94M pre-norm tap {i}: rel-L2 {r:.3e}")
         assert r <= LOOSE_REL, f"94M pre-norm tap {i}: rel-L2 {r:.3e}"
+
+
+def test_pipelined_host_calls(state_6m):
+    """anx_engine_forward_host_pipelined: back-to-back host-buffer forwards whose downloads overlap the next call;
+    two {device output, host output} sets alternate, a third and fourth call reuse them (the convs wait for the
+    download that still reads the buffer).  Every result equals the device-resident forward."""
+    eng = make_engine(CFG_6M, state_6m)
+    shape = (2, 1, 32, 32, 128)
+    xs = [rand_input(shape, 40 + i).pin_memory() for i in range(4)]
+    want = [eng.forward(x.cuda()).cpu() for x in xs]
+    dev_in = torch.empty(shape, device="cuda")
+    outs = [torch.empty((2, 16, 32, 32, 128), device="cuda") for _ in range(2)]
+    hosts = [torch.empty((2, 16, 32, 32, 128)).pin_memory() for _ in range(4)]
+    for i in range(4):
+        eng.forward_host_pipelined(xs[i], hosts[i], dev_in, outs[i % 2])
+    eng.host_wait()
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(hosts[i], want[i]), f"pipelined call {i} differs"
+    # a plain call afterwards still completes on the stream by itself
+    y = torch.empty((2, 16, 32, 32, 128)).pin_memory()
+    eng.forward_host(xs[0], y, dev_in, outs[0])
+    torch.cuda.synchronize()
+    assert torch.equal(y, want[0])
