@@ -107,6 +107,8 @@ struct ConvLayer {            // one nn.Conv3d of the Sequential, network order
     void *d_wpack = nullptr;  // 16-bit slabs (tensor-core convs) or fp32 [cin][27][cout] (CUDA-core stem)
     void *d_wstem = nullptr;  // stem on tensor cores: bf16 hi|lo images of B, [kq][half][3*ncols][8] each
     void *d_wrows = nullptr;  // 16 -> 16 row kernel: three B images [z rotation][dx][k half][144 rows][8] (conv_rows.cuh)
+    int alt_splits = 0;       // > 0: a second packing in 64-column channel splits, unfolded (small problems, see make_geom)
+    void *d_wpack_alt = nullptr;
     void *d_wtrim = nullptr;  // low-resolution decoder half: compact per-tap tiles of the non-zero column spans (resident B)
     size_t wtrim_bytes = 0;
     void *d_wstem_rows = nullptr;   // row-form stem (Cin = 1, 16 columns): three bf16 B images [z rotation][k half][144 rows][8]
@@ -253,6 +255,7 @@ void add_conv(anx_engine *e, int &module_index, int cin, int cout, int level, bo
     c.inorm = c.has_norm && d.norm_kind == ANX_NORM_INSTANCE;
     c.n_splits = c.ncols > 256 ? c.ncols / 256 : 1;
     c.ncols_split = c.ncols / c.n_splits;
+    c.alt_splits = (!stem && c.ncols >= 128 && c.ncols % 64 == 0) ? c.ncols / 64 : 0;
     module_index += 1 + (c.has_norm ? 1 : 0) + (c.has_act ? 1 : 0);
     Step s{};
     s.kind = stem ? STEP_STEM : STEP_CONV;
@@ -527,26 +530,48 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.dt = e->dt;
     g.fold = c.fold;
     g.groups = c.groups;
+    // Small problems on wide layers (the 16^3 / 8^3 levels, above all at the batch-2 call shape of the sliding-window
+    // predictor): few tiles, each a long serial chain of N = 128 / 256 MMAs, leave most SMs idle.  When the regular
+    // tiling fills less than half the SMs the launch uses the layer's second packing: unfolded 64-column channel
+    // splits, one plane per tile -- (ncols / 64) x more tiles, each with cheaper MMAs (consecutive CTAs share one
+    // activation brick in L2).  More MMA time per FLOP, so only then.
+    bool alt = false;
+    if (c.alt_splits > 0 && c.d_wpack_alt && !exp_env("ANX_NO_ALT_SPLITS")) {
+        // tiles of the alternative tiling (one plane each): taken only while they still fit one wave -- measured at
+        // batch 8 (256 tiles): conv34 0.060 -> 0.070 ms; at batch 2 (64 tiles): 0.059 -> 0.041 ms
+        const size_t alt_tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y) * D * N * c.alt_splits;
+        alt = alt_tiles <= (size_t)e->num_sms;
+    }
+    if (alt) {
+        g.ncols = 64;
+        g.n_splits = c.alt_splits;
+        g.fold = 0;
+        g.groups = 3;
+        g.alt = 1;
+    }
+    const bool fold = g.fold != 0;
+    const int n_splits = g.n_splits;
     g.cin_chunks = c.cin / 16;
     g.in_groups_total = in_groups_total;
     g.in_group_offset = 0;
     // Single-slab layers (one 16-channel chunk, folded dz, no channel split: the 16 -> 16 convs) use the
     // same B image for every tile: it is loaded once per CTA and stays in shared memory.
-    g.b_static = (c.fold && g.cin_chunks == 1 && c.n_splits == 1 && !exp_env("ANX_NO_BSTATIC")) ? 1 : 0;
+    g.b_static = (fold && g.cin_chunks == 1 && n_splits == 1 && !exp_env("ANX_NO_BSTATIC")) ? 1 : 0;
     // output planes per tile: as many as TMEM double buffering allows, at most 8 -- or 16 for the thin
     // single-slab layers, whose MMA count per output plane is 9 * (bz + 2) / bz (all of TMEM, two A stages)
     int bz = std::max(1, std::min(8, 256 / g.ncols));
     if (g.b_static && g.ncols == 16 && D >= 16 && !exp_env("ANX_NO_BZ16")) bz = 16;
     g.acc_stages = 2;
     bz = std::min(bz, D);
+    if (alt) bz = 1;
     // Unfolded (wide) layers at the deep levels: a tile is a long serial chain of MMAs (27 taps x Cin / 16 per
     // plane) and there are few tiles, so with two planes per tile most SMs idle while a few grind: one plane per
     // tile doubles the parallelism at no extra MMA work (unfolded tiles have no z halo cost in the MMAs).  Only
     // while the doubled tile count still fits one wave: every tile streams the layer's whole weight set from
     // L2, so past one wave the extra weight traffic costs more than the parallelism brings (measured at batch 8:
     // conv38 0.086 -> 0.110 ms with 256 tiles; at batch 2: 0.086 -> 0.060 ms with 64).
-    if (!c.fold && bz > 1 && !exp_env("ANX_NO_BZ1")) {
-        const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y) * ((D + bz - 1) / bz) * N * c.n_splits;
+    if (!fold && bz > 1 && !exp_env("ANX_NO_BZ1")) {
+        const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y) * ((D + bz - 1) / bz) * N * n_splits;
         if (2 * tiles <= (size_t)e->num_sms) bz = 1;
     }
     g.bz = bz;
@@ -562,11 +587,11 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     g.total_tiles = g.tiles_per_sample * N * g.n_splits;
     g.a_lbo = (uint32_t)(bz + 2) * HALO_Y * ROW_BYTES;
     g.a_stage_bytes = 2 * g.a_lbo;
-    g.b_rows = c.fold ? 3 * g.ncols : g.ncols;
+    g.b_rows = fold ? 3 * g.ncols : g.ncols;
     g.b_stage_bytes = 9 * 32 * g.b_rows;
     // InstanceNorm statistics of thin layers are accumulated per CTA in shared memory (one flush per sample instead
     // of one double atomic per warp, chunk and tile)
-    g.stats_acc = (c.inorm && g.ncols <= STATS_ACC_MAX_COLS && c.n_splits == 1) ? 1 : 0;
+    g.stats_acc = (c.inorm && g.ncols <= STATS_ACC_MAX_COLS && n_splits == 1) ? 1 : 0;
     const size_t shared_tail = sizeof(UmmaShared) + (g.stats_acc ? STATS_ACC_BYTES : 0);
     const size_t budget = (size_t)e->max_smem - shared_tail - 1024;
     g.a_stages = 3;
@@ -582,7 +607,7 @@ ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H,
     // Low-resolution half of a decoder conv: each tap's MMA covers just the span of its parities (trim_span); when the
     // compact tiles of the whole layer fit next to the A ring they stay resident in shared memory, loaded once per CTA
     // instead of streaming 221 KB of (mostly zero) slabs from L2 for every tile.
-    if (c.d2s_cout > 0 && !c.fold && c.n_splits == 1 && c.d2s_cout % 16 == 0 && !exp_env("ANX_NO_TRIM")) {
+    if (!alt && c.d2s_cout > 0 && !c.fold && c.n_splits == 1 && c.d2s_cout % 16 == 0 && !exp_env("ANX_NO_TRIM")) {
         g.trim = 1;
         const int blocks = c.d2s_cout / 16;        // 16-column blocks per parity
         uint32_t off16 = 0;
@@ -886,10 +911,10 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             ActView src = view_of(e, p, c.src_buf, 0);
             const size_t items = (size_t)g.N * g.D * g.H * g.W * (g.ncols * g.n_splits / 16);
             conv3_simt_kernel<<<grid_for(items, 128, e->num_sms, 64), 128, 0, st>>>(
-                src, g, (const __nv_bfloat16 *)c.d_wpack, ep);
+                src, g, (const __nv_bfloat16 *)(g.alt ? c.d_wpack_alt : c.d_wpack), ep);
         } else {
             const int grid = std::min(g.total_tiles, e->num_sms);
-            const uint8_t *wp_ = (const uint8_t *)(g.trim == 2 ? c.d_wtrim : c.d_wpack);
+            const uint8_t *wp_ = (const uint8_t *)(g.trim == 2 ? c.d_wtrim : (g.alt ? c.d_wpack_alt : c.d_wpack));
 #define ANX_CONV(MODE_) conv3_umma_kernel<MODE_><<<grid, UMMA_THREADS, g.smem_bytes, st>>>(p.tmaps[s.conv], g, wp_, ep)
             if (ep.mode == OUT_NCDHW_F32) {
                 if (ep.cl16) ANX_CONV(EPI_CL16);
@@ -1093,6 +1118,7 @@ void anx_engine_destroy(anx_engine *e) {
         if (c.d_wstem) cudaFree(c.d_wstem);
         if (c.d_wstem_rows) cudaFree(c.d_wstem_rows);
         if (c.d_wtrim) cudaFree(c.d_wtrim);
+        if (c.d_wpack_alt) cudaFree(c.d_wpack_alt);
         if (c.d_wrows) cudaFree(c.d_wrows);
         if (c.d_bias) cudaFree(c.d_bias);
     }
@@ -1101,6 +1127,7 @@ void anx_engine_destroy(anx_engine *e) {
         if (c.d_wstem) cudaFree(c.d_wstem);
         if (c.d_wstem_rows) cudaFree(c.d_wstem_rows);
         if (c.d_wtrim) cudaFree(c.d_wtrim);
+        if (c.d_wpack_alt) cudaFree(c.d_wpack_alt);
         if (c.d_wrows) cudaFree(c.d_wrows);
         if (c.d_bias) cudaFree(c.d_bias);
     }
@@ -1212,6 +1239,25 @@ static anx_status upload_conv(anx_engine *e, ConvLayer &c, const std::vector<flo
         c.wpack_bytes = pk.size() * sizeof(uint16_t);
         ANX_CUDA(e, cudaMalloc(&c.d_wpack, c.wpack_bytes));
         ANX_CUDA(e, cudaMemcpy(c.d_wpack, pk.data(), c.wpack_bytes, cudaMemcpyHostToDevice));
+        if (c.d_wpack_alt) { cudaFree(c.d_wpack_alt); c.d_wpack_alt = nullptr; }
+        if (c.alt_splits > 0 && !c.d2s_cout) {
+            // second packing for small problems (make_geom): 64-column splits, unfolded, one slab per dz
+            const int Wa = 64, nsp = c.alt_splits;
+            const size_t slab_a = (size_t)9 * 2 * Wa * 8;
+            std::vector<uint16_t> pa((size_t)nsp * chunks * 3 * slab_a, 0);
+            for (int o = 0; o < c.cout; ++o)
+                for (int i = 0; i < c.cin; ++i) {
+                    const int ch = i / 16, kc = (i % 16) / 8, el = i % 8, split = o / Wa, ol = o % Wa;
+                    for (int kz = 0; kz < 3; ++kz)
+                        for (int t = 0; t < 9; ++t) {
+                            const float v = w[((size_t)o * c.cin + i) * 27 + kz * 9 + t];
+                            pa[((size_t)(split * chunks + ch) * 3 + kz) * slab_a + ((size_t)(t * 2 + kc) * Wa + ol) * 8 + el] =
+                                e->dt == DT_BF16 ? f32_to_bf16_rne(v) : f32_to_f16_rne(v);
+                        }
+                }
+            ANX_CUDA(e, cudaMalloc(&c.d_wpack_alt, pa.size() * sizeof(uint16_t)));
+            ANX_CUDA(e, cudaMemcpy(c.d_wpack_alt, pa.data(), pa.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        }
         if (c.d_wrows) { cudaFree(c.d_wrows); c.d_wrows = nullptr; }
         if (c.fold && c.cin == 16 && c.ncols == 16 && c.n_splits == 1) {
             // conv3_rows_kernel: image r (= input plane mod 3), tap dx, K half, row (j*3 + s)*16 + co holds
@@ -1858,10 +1904,11 @@ anx_status anx_engine_set_tap_conv(anx_engine *e, int32_t k, const float *weight
     if (e->tap_convs.size() != e->logical.size()) e->tap_convs.resize(e->logical.size());
     ConvLayer &t = e->tap_convs[k];
     const ConvLayer &src = e->convs[L.conv_a];
-    void *keep[6] = {t.d_wpack, t.d_wstem, t.d_wrows, t.d_wtrim, t.d_wstem_rows, t.d_bias};   // upload_conv frees / replaces these
+    // the clone owns its device buffers: keep them across the struct copy (upload_conv frees / replaces them)
+    void *keep[7] = {t.d_wpack, t.d_wstem, t.d_wrows, t.d_wtrim, t.d_wstem_rows, t.d_bias, t.d_wpack_alt};
     t = src;
     t.d_wpack = keep[0]; t.d_wstem = keep[1]; t.d_wrows = keep[2]; t.d_wtrim = keep[3]; t.d_wstem_rows = keep[4];
-    t.d_bias = static_cast<float *>(keep[5]);
+    t.d_bias = static_cast<float *>(keep[5]); t.d_wpack_alt = keep[6];
     t.is_tap = true; t.is_final = true; t.has_norm = false; t.has_act = false; t.inorm = false;
     t.pool_dst_buf = -1; t.seed_buf = -1; t.d2s_cout = 0; t.dst_buf = -1; t.ready = false;
     const size_t nw = (size_t)L.cout * L.cin * 27;

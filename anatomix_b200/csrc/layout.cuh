@@ -150,6 +150,7 @@ struct ConvGeom {
     uint32_t smem_bytes;
     int fuse_pool;          // this launch also writes the pooled tensor (needs bz % 4 == 0)
     int b_static;           // 1: one B slab serves every tile; loaded once per CTA, never recycled
+    int alt;                // 1: the layer's second packing (64-column splits, unfolded) is in use for this small problem
     int stats_acc;          // EPI_STATS on a thin layer: per-warp sums in shared memory behind UmmaShared (STATS_ACC_BYTES more)
     uint32_t ablate;        // timing experiments only (ANX_ABLATE): 1 no MMA, 2 no stores, 4 no A load, 8 no B load,
                             // 16 every tap reads the brick origin, 32 128-byte aligned core matrices (results are wrong)
