@@ -521,6 +521,21 @@ void trim_span(int kz, int ky, int kx, int blocks, int &lo, int &n) {
     n = (pmax - pmin + 1) * blocks;
 }
 
+// Output planes per unit of the row kernels: a unit streams zs + 2 input planes, and units are dealt round-robin to
+// the persistent CTAs, so the launch takes ceil(units / SMs) * (zs + 2) plane times.  Longer z segments have less halo
+// but fewer units: pick the segment length (a divisor of D among 16, 32, 64) that minimises that product.
+int rows_segment(const anx_engine *e, int N, int D, int H, int W) {
+    int best = 16;
+    size_t best_cost = ~(size_t)0;
+    for (int zs : {16, 32, 64}) {
+        if (D % zs) continue;
+        const size_t units = (size_t)N * (W / ROWS_X) * (H / ROWS_YB) * (D / zs);
+        const size_t cost = ((units + e->num_sms - 1) / e->num_sms) * (size_t)(zs + 2);
+        if (cost < best_cost) { best_cost = cost; best = zs; }
+    }
+    return best;
+}
+
 // Tile / pipeline configuration of one tensor-core conv at one shape.
 ConvGeom make_geom(const anx_engine *e, const ConvLayer &c, int N, int D, int H, int W, int in_groups_total) {
     ConvGeom g{};
@@ -788,7 +803,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             // row-form stem: the 16 -> 16 row kernel's pipeline with builder warps in front of it
             RowsGeom rg{};
             rg.N = p.N; rg.D = p.D; rg.H = p.H; rg.W = p.W;
-            rg.zs = 16;
+            rg.zs = rows_segment(e, p.N, p.D, p.H, p.W);
             rg.tiles_x = p.W / ROWS_X; rg.tiles_y = p.H / ROWS_YB; rg.tiles_z = p.D / rg.zs;
             rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
             rg.total_units = rg.units_per_sample * p.N;
@@ -885,7 +900,7 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             !(ep.cl16 && c.cout != 16) && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
             RowsGeom rg{};
             rg.N = g.N; rg.D = g.D; rg.H = g.H; rg.W = g.W;
-            rg.zs = 16;
+            rg.zs = rows_segment(e, g.N, g.D, g.H, g.W);
             rg.tiles_x = g.W / ROWS_X; rg.tiles_y = g.H / ROWS_YB; rg.tiles_z = g.D / rg.zs;
             rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
             rg.total_units = rg.units_per_sample * g.N;
