@@ -120,7 +120,10 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         const int tz = r / (g.tiles_y * g.tiles_x);
         r -= tz * g.tiles_y * g.tiles_x;
         const int ty = r / g.tiles_x;
+        // the last x tile of a width that is not a multiple of 128 is pulled back to end at the border: it recomputes
+        // (and re-stores, identically) the voxels it shares with its left neighbour -- no masked lanes anywhere
         x0 = (r - ty * g.tiles_x) * ROWS_X;
+        if (x0 + ROWS_X > g.W) x0 = g.W - ROWS_X;
         y0 = ty * ROWS_YB;
         z0 = tz * g.zs;
     };

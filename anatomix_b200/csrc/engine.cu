@@ -524,12 +524,16 @@ void trim_span(int kz, int ky, int kx, int blocks, int &lo, int &n) {
 // Output planes per unit of the row kernels: a unit streams zs + 2 input planes, and units are dealt round-robin to
 // the persistent CTAs, so the launch takes ceil(units / SMs) * (zs + 2) plane times.  Longer z segments have less halo
 // but fewer units: pick the segment length (a divisor of D among 16, 32, 64) that minimises that product.
+// Widths the row kernels take: whole 128-voxel x tiles, or a last tile pulled back to the border when the voxels it
+// recomputes are at most a fifth of the row (224 = 128 + 96: 14 % extra work beats the generic tile kernel; 160 does not).
+bool rows_width_ok(int W) { return W >= ROWS_X && ((W + ROWS_X - 1) / ROWS_X) * ROWS_X * 5 <= W * 6; }
+
 int rows_segment(const anx_engine *e, int N, int D, int H, int W) {
     int best = 16;
     size_t best_cost = ~(size_t)0;
     for (int zs : {16, 32, 64}) {
         if (D % zs) continue;
-        const size_t units = (size_t)N * (W / ROWS_X) * (H / ROWS_YB) * (D / zs);
+        const size_t units = (size_t)N * ((W + ROWS_X - 1) / ROWS_X) * (H / ROWS_YB) * (D / zs);
         const size_t cost = ((units + e->num_sms - 1) / e->num_sms) * (size_t)(zs + 2);
         if (cost < best_cost) { best_cost = cost; best = zs; }
     }
@@ -798,13 +802,13 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
         const ConvLayer &c = conv_override ? *conv_override : e->convs[s.conv];
         Epilogue ep = make_epilogue(e, p, c, out);
         const int zh0 = (e->desc.flags & ANX_FLAG_DEPTH_HALO_INPUT) ? 1 : 0;
-        if (!force_simt && e->use_rows && c.d_wstem_rows && !ep.stats && p.W % ROWS_X == 0 && p.H % ROWS_YB == 0 &&
+        if (!force_simt && e->use_rows && c.d_wstem_rows && !ep.stats && rows_width_ok(p.W) && p.H % ROWS_YB == 0 &&
             p.D % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !exp_env("ANX_NO_STEM_ROWS")) {
             // row-form stem: the 16 -> 16 row kernel's pipeline with builder warps in front of it
             RowsGeom rg{};
             rg.N = p.N; rg.D = p.D; rg.H = p.H; rg.W = p.W;
             rg.zs = rows_segment(e, p.N, p.D, p.H, p.W);
-            rg.tiles_x = p.W / ROWS_X; rg.tiles_y = p.H / ROWS_YB; rg.tiles_z = p.D / rg.zs;
+            rg.tiles_x = (p.W + ROWS_X - 1) / ROWS_X; rg.tiles_y = p.H / ROWS_YB; rg.tiles_z = p.D / rg.zs;
             rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
             rg.total_units = rg.units_per_sample * p.N;
             rg.dt = e->dt;
@@ -897,11 +901,11 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             return e->fail(ANX_ERR_UNSUPPORTED, "the 16-bit channels-last output needs the tensor-core path and output_nc % 8 == 0");
         if (!force_simt && e->use_rows && c.d_wrows && !(g.fuse_pool && ep.pool_kind != 0) && !ep.stats && !ep.d2s_cout &&
             !((e->use_rows & 2) && (g.fuse_pool || ep.seed_on)) &&      // ANX_ROWS=3: plain / fp32 variants only
-            !(ep.cl16 && c.cout != 16) && g.W % ROWS_X == 0 && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
+            !(ep.cl16 && c.cout != 16) && rows_width_ok(g.W) && g.H % ROWS_YB == 0 && g.D % 16 == 0) {
             RowsGeom rg{};
             rg.N = g.N; rg.D = g.D; rg.H = g.H; rg.W = g.W;
             rg.zs = rows_segment(e, g.N, g.D, g.H, g.W);
-            rg.tiles_x = g.W / ROWS_X; rg.tiles_y = g.H / ROWS_YB; rg.tiles_z = g.D / rg.zs;
+            rg.tiles_x = (g.W + ROWS_X - 1) / ROWS_X; rg.tiles_y = g.H / ROWS_YB; rg.tiles_z = g.D / rg.zs;
             rg.units_per_sample = rg.tiles_x * rg.tiles_y * rg.tiles_z;
             rg.total_units = rg.units_per_sample * g.N;
             rg.dt = e->dt;

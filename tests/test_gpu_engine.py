@@ -521,7 +521,8 @@ def test_native_blend_kernel_matches_torch_accumulate():
     assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256), (3, 1, 16, 8, 128), (1, 1, 48, 40, 128)])
+@pytest.mark.parametrize("shape", [(1, 1, 16, 16, 128), (2, 1, 32, 24, 256), (3, 1, 16, 8, 128), (1, 1, 48, 40, 128),
+                                   (1, 1, 16, 16, 224)])      # 224 = one whole x tile + one pulled back to the border
 def test_row_kernel_matches_generic_kernel(shape):
     """conv3_rows_kernel (dy and dz folded into N, lanes = one 128-voxel row) against the generic tile kernel
     on the same packed 16-bit operands: only the fp32 summation order differs."""
@@ -763,7 +764,8 @@ def test_zero_copy_concat_behind_other_features(state_6m, shape):
     assert got.shape == want.shape and torch.equal(got, want)
 
 
-@pytest.mark.parametrize("shape,halo", [((2, 1, 32, 32, 128), False), ((1, 1, 16, 8, 256), False), ((1, 1, 32, 16, 128), True)])
+@pytest.mark.parametrize("shape,halo", [((2, 1, 32, 32, 128), False), ((1, 1, 16, 8, 256), False), ((1, 1, 32, 16, 128), True),
+                                        ((1, 1, 16, 16, 240), False)])     # last x tile pulled back to the border
 def test_row_form_stem_matches_tile_form_stem(shape, halo):
     """The first conv in row form (conv3_rows_kernel<.., STEM>: one N = 144 MMA per input row, K = the three dx taps of
     the hi / lo split) against the tile-form stem kernel and the fp32 oracle conv: both keep fp32-level accuracy, so the
