@@ -39,6 +39,11 @@ constexpr int ROWS_B_TAP_BYTES = 2 * ROWS_N * 16;
 constexpr int ROWS_B_IMAGE_BYTES = 3 * ROWS_B_TAP_BYTES;        // three dx taps
 constexpr int ROWS_STRIP_COLS = ROWS_BY * 48;   // TMEM columns of one strip
 constexpr int ROWS_THREADS = 64 + 32 * 8;
+// Epilogue warps: (TMEM lane quadrant) x (row group of RPW output rows of each strip).  RPW = 2: eight warps, each
+// draining a row pair (needed by the fused pooling, whose y pair is the warp's two rows); RPW = 1: sixteen warps with
+// one row each -- the drain is a latency chain per warp (tcgen05.ld, re-seed, pack, stores, barrier round trip), so
+// twice the warps hide twice the latency (ablation at batch 4: 66 us of a 121 us launch is that skeleton).
+__host__ __device__ constexpr int rows_threads(int rpw, bool stem) { return 64 + 32 * (16 / rpw) + (stem ? 128 : 0); }
 // Stem variant (C_in = 1, fp32 NCDHW input): four builder warps (thread = x voxel) write the A tiles, see below.
 constexpr int ROWS_STEM_THREADS = ROWS_THREADS + 128;
 constexpr int ROWS_STEM_TILE_BYTES = 2 * ROWS_X * 16;           // one input row: two K halves x 128 lanes x 16 B
@@ -82,8 +87,8 @@ static_assert(offsetof(RowsShared, shift) % 16 == 0, "shift must be 16-byte alig
 // N = 144 MMA per input row replaces the three dx instructions of the 16-channel layers.  Four builder warps
 // (thread = x voxel) read the fp32 rows straight from global memory (reflect padding by index arithmetic) and write
 // the canonical K-major A tiles into the plane ring; MMA issue, TMEM layout and epilogue are the shared code.
-template <int MODE, bool STEM = false>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 (also the fused gather), EPI_CL16 or EPI_F32_HEAD
-__global__ void __launch_bounds__(STEM ? ROWS_STEM_THREADS : ROWS_THREADS, 1)
+template <int MODE, bool STEM = false, int RPW = 2>   // EPI_PADDED, EPI_POOL (max), EPI_SEEDED, EPI_F32 (also the fused gather), EPI_CL16 or EPI_F32_HEAD
+__global__ void __launch_bounds__(rows_threads(RPW, STEM), 1)
 conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict__ wrows, const Epilogue ep,
                   const float *__restrict__ stem_in) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,7 +104,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         for (int i = 0; i < ROWS_STAGES; ++i) { mbar_init(&sh->full_a[i], STEM ? 128 : 1); mbar_init(&sh->empty_a[i], 1); }
         mbar_init(&sh->full_b, 1);
         for (int i = 0; i < ROWS_STEM_IN_STAGES; ++i) { mbar_init(&sh->full_in[i], 1); mbar_init(&sh->empty_in[i], 128); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&sh->acc_ready[i >> 1][i & 1], 1); mbar_init(&sh->drained[i >> 1][i & 1], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&sh->acc_ready[i >> 1][i & 1], 1); mbar_init(&sh->drained[i >> 1][i & 1], 4 * (2 / RPW)); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -184,9 +189,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
             }
         }
         __syncwarp();
-    } else if (STEM && warp >= 10) {
+    } else if (STEM && warp >= 2 + 16 / RPW) {
         // ------------------------------------------------- stem: A-tile builders
-        const int bx = threadIdx.x - ROWS_THREADS;            // x voxel of the 128-wide tile
+        const int bx = threadIdx.x - rows_threads(RPW, false);   // x voxel of the 128-wide tile
         const int Ww = g.W;
         const uint8_t *stage0 = b_img + 3 * ROWS_STEM_B_IMAGE_BYTES;
         uint32_t ka = 0;
@@ -289,7 +294,9 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         constexpr bool POOL = MODE == EPI_POOL;
         constexpr bool PADDED = MODE == EPI_PADDED || SEEDED || POOL;
         const int q = warp & 3;                    // TMEM lane quadrant
-        const int h = (warp - 2) >> 2;             // rows {2h, 2h + 1} of each strip
+        static_assert(RPW == 2 || MODE != EPI_POOL, "the fused pooling needs a row pair per warp");
+        const int h = (warp - 2) >> 2;             // row group: rows {RPW * h + r} of each strip
+        const int pair = RPW == 2 ? h : h >> 1;    // the strip's row pair these rows belong to (hand-over barriers)
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int lx = q * 32 + lane;
         const int Dd = g.D, Hh = g.H, Ww = g.W;
@@ -327,11 +334,11 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
             int n, x0, y0, z0;
             decode(blockIdx.x < g.total_units ? blockIdx.x : 0, n, x0, y0, z0);
             for (int s = 0; s < 2; ++s)
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < RPW; ++r) {
                     uint4 s0, s1;
-                    load_seed(blockIdx.x < g.total_units, n, z0, y0 + s * ROWS_BY + 2 * h + r, x0 + lx, s0, s1);
+                    load_seed(blockIdx.x < g.total_units, n, z0, y0 + s * ROWS_BY + RPW * h + r, x0 + lx, s0, s1);
                     for (int slot = 0; slot < 3; ++slot) {
-                        const uint32_t col = lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + slot) * 16;
+                        const uint32_t col = lane_base + s * ROWS_STRIP_COLS + ((RPW * h + r) * 3 + slot) * 16;
                         if (slot == 0) seed_store(col, s0, s1);
                         else tmem_st16(col, sd);
                     }
@@ -340,7 +347,7 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&sh->drained[0][h]); mbar_arrive(&sh->drained[1][h]); }
+        if (lane == 0) { mbar_arrive(&sh->drained[0][pair]); mbar_arrive(&sh->drained[1][pair]); }
 
         uint32_t held[2][8];                        // POOL: row-pair maxima of the even plane of a z pair, per strip
 #pragma unroll
@@ -352,17 +359,17 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
         // next: o + 3 of the same unit, or plane 0 of the next unit after the last plane.  They are loaded one
         // drain ahead (`nsq`), so the L2 / HBM latency hides behind a drain's worth of work.
         auto seeds_for = [&](int p_, int s_, int n_, int x0_, int y0_, int z0_, bool nvalid, int nn_, int nx0_, int ny0_,
-                             int nz0_, uint4 (&out)[2][2]) {
+                             int nz0_, uint4 (&out)[RPW][2]) {
             const int o_ = p_ - 2;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int yo = s_ * ROWS_BY + 2 * h + r;
+            for (int r = 0; r < RPW; ++r) {
+                const int yo = s_ * ROWS_BY + RPW * h + r;
                 if (o_ + 3 < g.zs) load_seed(true, n_, z0_ + o_ + 3, y0_ + yo, x0_ + lx, out[r][0], out[r][1]);
                 else if (o_ == g.zs - 1) load_seed(nvalid, nn_, nz0_, ny0_ + yo, nx0_ + lx, out[r][0], out[r][1]);
                 else load_seed(false, 0, 0, 0, 0, out[r][0], out[r][1]);
             }
         };
-        uint4 nsq[2][2];
+        uint4 nsq[RPW][2];
         if constexpr (SEEDED) {
             int n, x0, y0, z0;
             decode(blockIdx.x < g.total_units ? blockIdx.x : 0, n, x0, y0, z0);
@@ -389,21 +396,21 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     // seeds of the plane that uses this slot next: o + 3 of this unit, or plane 0 of the next unit
-                    uint4 sq[2][2];
+                    uint4 sq[RPW][2];
                     if constexpr (SEEDED) {
 #pragma unroll
-                        for (int r = 0; r < 2; ++r) { sq[r][0] = nsq[r][0]; sq[r][1] = nsq[r][1]; }
+                        for (int r = 0; r < RPW; ++r) { sq[r][0] = nsq[r][0]; sq[r][1] = nsq[r][1]; }
                         // the drain after this one: the other strip, the next plane, or the first drain of the next unit
                         if (s == 0) seeds_for(p, 1, n, x0, y0, z0, nvalid, nn, nx0, ny0, nz0, nsq);
                         else if (p + 1 < planes) seeds_for(p + 1, 0, n, x0, y0, z0, nvalid, nn, nx0, ny0, nz0, nsq);
                         else if (nvalid) seeds_for(0, 0, nn, nx0, ny0, nz0, false, 0, 0, 0, 0, nsq);
                     }
-                    mbar_wait(&sh->acc_ready[s][h], ka & 1, 25);
+                    mbar_wait(&sh->acc_ready[s][pair], ka & 1, 25);
                     tc_fence_after();
                     uint32_t pm[8];                                // POOL: maximum over this warp's two rows
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int yo = 2 * h + r;
+                    for (int r = 0; r < RPW; ++r) {
+                        const int yo = RPW * h + r;
                         const uint32_t col = lane_base + s * ROWS_STRIP_COLS + (yo * 3 + slot) * 16;
                         __syncwarp();
                         if (o < 0) {                               // phantom plane below the segment: discard
@@ -509,17 +516,17 @@ conv3_rows_kernel(const ActView src, const RowsGeom g, const uint8_t *__restrict
                     }
                     if (p == planes - 1) {          // phantom planes above the segment: neutral again
 #pragma unroll
-                        for (int r = 0; r < 2; ++r)
+                        for (int r = 0; r < RPW; ++r)
 #pragma unroll
                             for (int e = 1; e <= 2; ++e) {
                                 __syncwarp();
-                                tmem_st16(lane_base + s * ROWS_STRIP_COLS + ((2 * h + r) * 3 + (slot + e) % 3) * 16, sd);
+                                tmem_st16(lane_base + s * ROWS_STRIP_COLS + ((RPW * h + r) * 3 + (slot + e) % 3) * 16, sd);
                             }
                     }
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh->drained[s][h]);
+                    if (lane == 0) mbar_arrive(&sh->drained[s][pair]);
                 }
             }
         }

@@ -174,6 +174,8 @@ struct anx_engine {
     anx_unet_desc desc;
     int dt = DT_BF16;         // storage type of activations / packed weights
     int use_rows = 1;         // thin 16 -> 16 layers run on conv3_rows_kernel when the shape allows (ANX_ROWS=0: never)
+    int rows_rpw1 = 0;        // row-kernel variants that run 16 one-row epilogue warps instead of 8 row-pair warps:
+                              // bit 0 plain padded store, 1 stem, 2 seeded, 3 fp32 / 16-bit / head outputs
     int x_lead = 0;           // row layout of the padded planar buffers (layout.cuh layout_of; ANX_X_LEAD)
     int num_sms = 148;
     int max_smem = 0;
@@ -524,6 +526,8 @@ void trim_span(int kz, int ky, int kx, int blocks, int &lo, int &n) {
 // Output planes per unit of the row kernels: a unit streams zs + 2 input planes, and units are dealt round-robin to
 // the persistent CTAs, so the launch takes ceil(units / SMs) * (zs + 2) plane times.  Longer z segments have less halo
 // but fewer units: pick the segment length (a divisor of D among 16, 32, 64) that minimises that product.
+constexpr int ROWS_RPW1_DEFAULT = 1 | 2 | 4;   // see anx_engine::rows_rpw1 (measured: padded -4 %, stem -14 %, seeded -15 %, fp32 +7 %)
+
 // Widths the row kernels take: whole 128-voxel x tiles, or a last tile pulled back to the border when the voxels it
 // recomputes are at most a fifth of the row (224 = 128 + 96: 14 % extra work beats the generic tile kernel; 160 does not).
 bool rows_width_ok(int W) { return W >= ROWS_X && ((W + ROWS_X - 1) / ROWS_X) * ROWS_X * 5 <= W * 6; }
@@ -819,6 +823,9 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             if (ep.mode == OUT_NCDHW_F32)      // pre-norm tap of the stem
                 conv3_rows_kernel<EPI_F32, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
                     ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
+            else if (e->rows_rpw1 & 2)
+                conv3_rows_kernel<EPI_PADDED, true, 1><<<grid, rows_threads(1, true), rg.smem_bytes, st>>>(
+                    ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
             else
                 conv3_rows_kernel<EPI_PADDED, true><<<grid, ROWS_STEM_THREADS, rg.smem_bytes, st>>>(
                     ActView{}, rg, (const uint8_t *)c.d_wstem_rows, ep, in);
@@ -915,15 +922,18 @@ anx_status launch_step(anx_engine *e, const ShapePlan &p, const Step &s, const f
             const int grid = std::min(rg.total_units, e->num_sms);
             const uint8_t *wr = (const uint8_t *)c.d_wrows;
 #define ANX_ROWS_LAUNCH(MODE_) conv3_rows_kernel<MODE_><<<grid, ROWS_THREADS, rg.smem_bytes, st>>>(src, rg, wr, ep, nullptr)
+#define ANX_ROWS_LAUNCH1(MODE_) conv3_rows_kernel<MODE_, false, 1><<<grid, rows_threads(1, false), rg.smem_bytes, st>>>(src, rg, wr, ep, nullptr)
             if (ep.mode == OUT_NCDHW_F32) {
-                if (ep.head_nc > 0) ANX_ROWS_LAUNCH(EPI_F32_HEAD);
-                else if (ep.cl16) ANX_ROWS_LAUNCH(EPI_CL16);
-                else ANX_ROWS_LAUNCH(EPI_F32);       // also the fused gather (peer loop inside)
+                const bool one = (e->rows_rpw1 & 8) != 0;
+                if (ep.head_nc > 0) { if (one) ANX_ROWS_LAUNCH1(EPI_F32_HEAD); else ANX_ROWS_LAUNCH(EPI_F32_HEAD); }
+                else if (ep.cl16) { if (one) ANX_ROWS_LAUNCH1(EPI_CL16); else ANX_ROWS_LAUNCH(EPI_CL16); }
+                else { if (one) ANX_ROWS_LAUNCH1(EPI_F32); else ANX_ROWS_LAUNCH(EPI_F32); }   // also the fused gather (peer loop inside)
             }
-            else if (ep.seed_on) ANX_ROWS_LAUNCH(EPI_SEEDED);
+            else if (ep.seed_on) { if (e->rows_rpw1 & 4) ANX_ROWS_LAUNCH1(EPI_SEEDED); else ANX_ROWS_LAUNCH(EPI_SEEDED); }
             else if (g.fuse_pool) ANX_ROWS_LAUNCH(EPI_POOL);
-            else ANX_ROWS_LAUNCH(EPI_PADDED);
+            else { if (e->rows_rpw1 & 1) ANX_ROWS_LAUNCH1(EPI_PADDED); else ANX_ROWS_LAUNCH(EPI_PADDED); }
 #undef ANX_ROWS_LAUNCH
+#undef ANX_ROWS_LAUNCH1
             break;
         }
         if (force_simt) {
@@ -1082,6 +1092,8 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     e->max_smem = (int)prop.sharedMemPerBlockOptin;
     if (const char *xl = exp_env("ANX_X_LEAD")) e->x_lead = atoi(xl);
     if (desc->flags & ANX_FLAG_NO_ROWS) e->use_rows = 0;
+    e->rows_rpw1 = ROWS_RPW1_DEFAULT;
+    if (const char *rp = exp_env("ANX_RPW1")) e->rows_rpw1 = atoi(rp);
     if (const char *rw = exp_env("ANX_ROWS")) e->use_rows = atoi(rw);
     build_program(e);
     build_taps(e);
@@ -1102,6 +1114,9 @@ anx_status anx_engine_create(const anx_unet_desc *desc, anx_engine **out) {
     ANX_SMEM((stem_umma_kernel<1, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<2, EPI_STATS>)); ANX_SMEM((stem_umma_kernel<3, EPI_STATS>));
     ANX_SMEM((stem_umma_kernel<1, EPI_F32>)); ANX_SMEM((stem_umma_kernel<2, EPI_F32>)); ANX_SMEM((stem_umma_kernel<3, EPI_F32>));
     ANX_SMEM((conv3_rows_kernel<EPI_F32, true>));
+    ANX_SMEM((conv3_rows_kernel<EPI_PADDED, false, 1>)); ANX_SMEM((conv3_rows_kernel<EPI_PADDED, true, 1>));
+    ANX_SMEM((conv3_rows_kernel<EPI_SEEDED, false, 1>)); ANX_SMEM((conv3_rows_kernel<EPI_F32, false, 1>));
+    ANX_SMEM((conv3_rows_kernel<EPI_CL16, false, 1>)); ANX_SMEM((conv3_rows_kernel<EPI_F32_HEAD, false, 1>));
 #undef ANX_SMEM
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(stem_conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
