@@ -77,12 +77,28 @@ def weights_94m():
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) of the tcgen05 conv launches of one 8x128^3 forward, from the newest committed
-    ncu --set full capture under profiles/; None when missing."""
+    ncu --set full capture under profiles/; None when missing.  Third value: the per-launch list of that capture."""
     for name in ("r2_traffic.json", "r1_traffic.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
-            return json.load(open(path)).get("conv3_umma_kernel_dram_bytes_per_step"), name
-    return None, None
+            d = json.load(open(path))
+            return d.get("conv3_umma_kernel_dram_bytes_per_step"), name, d.get("per_launch")
+    return None, None, None
+
+
+def hbm_side(acc, order, per_launch, peaks, batch):
+    """The memory-bound stages (the level-0 launches): DRAM bytes per launch from the committed ncu
+    capture (a property of the kernel and the shape, batch 8) over the launch time measured live in this run."""
+    tc = [n for n in order if "conv" in n]              # the tcgen05 launches of one forward, in launch order
+    if not per_launch or len(per_launch) != len(tc) or batch != BATCH:
+        return None
+    out = {}
+    for n, pl in zip(tc, per_launch):
+        if n.endswith("_L0") and acc[n] > 0:
+            gbs = pl["dram_gb"] / (acc[n] / 1e3)
+            out[n] = {"dram_gb_ncu": pl["dram_gb"], "ms_live": round(acc[n], 4), "gbs": round(gbs, 1),
+                      "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    return {"hbm_peak_gbs": peaks["hbm"], "launches": out}
 
 
 def synth(n, seed, size=VOL):
@@ -222,7 +238,8 @@ def is_tc_conv(name):       # launches of the two tcgen05 conv kernels (the stem
     return "conv" in name and not name.startswith("conv0_")
 
 
-def roofline_block(acc, order, gflop_vol, gflop_stem, mb_vol, ceiling, batch, vol_s, peaks, traffic=None, traffic_src=None):
+def roofline_block(acc, order, gflop_vol, gflop_stem, mb_vol, ceiling, batch, vol_s, peaks, traffic=None, traffic_src=None,
+                   per_launch=None):
     conv_ms = sum(t for n, t in acc.items() if is_tc_conv(n))
     fwd_ms = sum(acc.values())
     achieved = (gflop_vol - gflop_stem) * 1e9 * batch / (conv_ms / 1e3) / 1e12
@@ -233,6 +250,7 @@ def roofline_block(acc, order, gflop_vol, gflop_stem, mb_vol, ceiling, batch, vo
             "peak_source": peaks["source"] + " bf16_tflops (burst: the timed region is short and runs at full SM clock)",
             "frac_of_sustained_peak": achieved / peaks["tf_sustained"], "sustained_peak": peaks["tf_sustained"],
             "traffic": traffic, "traffic_source": traffic_src,
+            "memory_bound_launches": hbm_side(acc, order, per_launch, peaks, batch),
             "whole_forward": {"ms_sum_of_launches": fwd_ms,
                               "hbm_gbs_algorithmic": mb_vol * 1e6 * batch / (fwd_ms / 1e3) / 1e9, "hbm_peak": peaks["hbm"],
                               "ceiling_vol_s": ceiling, "frac_of_ceiling": vol_s / ceiling}}
@@ -698,7 +716,7 @@ def main():
         else:
             value, ms_step, clocks = value_compute, ms_total / args.steps, clocks_compute
             par = "single GPU"
-        traffic, traffic_src = ncu_traffic_bytes()
+        traffic, traffic_src, per_launch = ncu_traffic_bytes()
         line = {
             "metric": "volumes/sec (128^3 1->16ch UNet forward)", "value": value, "unit": "volumes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -723,7 +741,7 @@ def main():
             "gpu_launches": eng.launches_per_forward(B, VOL, VOL, VOL) * args.steps,
             "clocks": clocks,
             "roofline": roofline_block(acc, order, GFLOP_6M, GFLOP_6M_STEM, MB_6M, CEIL_6M, B, value_compute / world,
-                                       peaks, traffic, traffic_src),
+                                       peaks, traffic, traffic_src, per_launch),
             "launch_ms": {n: round(acc[n], 4) for n in order},
         }
         if world > 1:

@@ -1,5 +1,6 @@
 """Turns the raw outputs of tools/round_profiles.sh (gpurun_out/final/) into the committed profiles/r2_* files.
     python tools/make_profiles.py"""
+import re
 import collections, csv, json, os, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 F, P = os.path.join(ROOT, "gpurun_out", "final") + "/", os.path.join(ROOT, "profiles") + "/"
@@ -70,7 +71,7 @@ def traffic(r):
 
 
 data = rows[2:]
-stem = [r for r in data if "conv3_rows_kernel<0, 1>" in r[ki] or "stem_umma" in r[ki]]
+stem = [r for r in data if re.search(r"conv3_rows_kernel<\d+, 1[,>]", r[ki]) or "stem_umma" in r[ki]]   # <MODE, STEM = 1, ...>
 conv = [r for r in data if r not in stem]
 json.dump({"source": "ncu --set full --clock-control none over the tcgen05 launches of one 8x128^3 forward (tools/round_profiles.sh)",
            "conv_launches": len(conv), "conv3_umma_kernel_dram_bytes_per_step": sum(traffic(r) for r in conv),
