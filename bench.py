@@ -86,6 +86,10 @@ def ncu_traffic_bytes():
     return None, None, None
 
 
+# SURVEY Appendix A.1, MB per volume of the layers it marks memory-bound (bf16 intermediates, fp32 network input / output)
+ALGO_MB_MEMORY_BOUND = {"conv0": 75.5, "conv3": 134.2, "conv6": 134.2, "conv62": 134.2, "conv65": 201.3}
+
+
 def hbm_side(acc, order, per_launch, peaks, batch):
     """The memory-bound stages (the level-0 launches): DRAM bytes per launch from the committed ncu
     capture (a property of the kernel and the shape, batch 8) over the launch time measured live in this run."""
@@ -98,6 +102,10 @@ def hbm_side(acc, order, per_launch, peaks, batch):
             gbs = pl["dram_gb"] / (acc[n] / 1e3)
             out[n] = {"dram_gb_ncu": pl["dram_gb"], "ms_live": round(acc[n], 4), "gbs": round(gbs, 1),
                       "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+            mb = ALGO_MB_MEMORY_BOUND.get(n.split("_")[0])
+            if mb:      # the same launch against SURVEY's fused-minimum bytes of that layer
+                out[n]["algorithmic_gb"] = round(mb * batch / 1e3, 4)
+                out[n]["frac_of_hbm_peak_algorithmic"] = round(mb * 1e6 * batch / (acc[n] / 1e3) / 1e9 / peaks["hbm"], 3)
     return {"hbm_peak_gbs": peaks["hbm"], "launches": out}
 
 

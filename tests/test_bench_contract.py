@@ -70,6 +70,9 @@ def test_memory_bound_launch_view_follows_launch_order():
     assert set(out["launches"]) == {"conv0_1to16_L0", "conv3_16to16_L0", "conv65_16to16_L0"}
     assert out["launches"]["conv65_16to16_L0"]["gbs"] == pytest.approx(1.6 / 0.2e-3, rel=1e-3)
     assert out["launches"]["conv3_16to16_L0"]["frac_of_hbm_peak"] == pytest.approx(5000.0 / 6500.0, abs=1e-3)
+    # SURVEY's fused-minimum bytes of the layer (134.2 MB per volume for a 16 -> 16 conv at 128^3) over the same time
+    assert out["launches"]["conv3_16to16_L0"]["frac_of_hbm_peak_algorithmic"] == pytest.approx(
+        134.2e6 * b.BATCH / 0.2e-3 / 1e9 / 6500.0, abs=1e-3)
     # a capture of another shape (other launch count) or batch is not used
     assert b.hbm_side(acc, order, per_launch[:-1], {"hbm": 6500.0}, b.BATCH) is None
     assert b.hbm_side(acc, order, per_launch, {"hbm": 6500.0}, 2) is None
